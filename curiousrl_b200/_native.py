@@ -1,0 +1,97 @@
+"""ctypes binding of the C ABI declared in include/curiousrl_b200.h.
+
+There is no CPU path behind these calls: if the library cannot be loaded, or no CUDA device
+is present when a compute entry point is called, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+from . import build as _build
+
+MODEL_IDS = {"TwoLinkPlanarManipulator": 0, "ThreeLinkPlanarManipulator": 1, "RoboticArmTracking": 2}
+DTYPE_IDS = {"float64": 0, "float32": 1}
+LINE_SEARCH_IDS = {"vanilla": 0, "feasibility": 1, "none": 2}
+STOPPING_IDS = {"relative": 0, "vanilla": 1}
+
+# every symbol include/curiousrl_b200.h declares (tests check the library exports all of them)
+EXPORTS = ("crl_abi_version", "crl_status_string", "crl_model_dims", "crl_model_default_bounds", "crl_rollout",
+           "crl_cost", "crl_derivs", "crl_backward", "crl_backward_dense", "crl_update_traj", "crl_forward_pass",
+           "crl_solve_workspace_bytes", "crl_solve")
+
+
+class Problem(Structure):
+    _fields_ = [("model", c_int32), ("dtype", c_int32), ("batch", c_int64), ("horizon", c_int32),
+                ("params_stride_t", c_int32), ("params_stride_b", c_int64), ("params", c_void_p),
+                ("u_lo", c_double), ("u_hi", c_double)]
+
+
+class SolverOpts(Structure):
+    _fields_ = [("max_iter", c_int32), ("is_check_stop", c_int32), ("stopping_criterion", c_double),
+                ("max_line_search", c_int32), ("gamma", c_double), ("line_search_method", c_int32),
+                ("stopping_method", c_int32), ("grid_blocks", c_int32), ("reserved", c_int32)]
+
+
+_lib = None
+
+
+def _declare(lib):
+    P, O = POINTER(Problem), POINTER(SolverOpts)
+    vp = c_void_p
+    lib.crl_abi_version.restype = c_int
+    lib.crl_status_string.restype = c_char_p
+    lib.crl_status_string.argtypes = [c_int]
+    lib.crl_model_dims.argtypes = [c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]
+    lib.crl_model_default_bounds.argtypes = [c_int, POINTER(c_double), POINTER(c_double)]
+    lib.crl_rollout.argtypes = [P, vp, vp, c_int64, vp, vp, vp]
+    lib.crl_cost.argtypes = [P, vp, vp, vp]
+    lib.crl_derivs.argtypes = [P, vp, vp, vp, vp, vp]
+    lib.crl_backward.argtypes = [P, vp, vp, vp, vp]
+    lib.crl_backward_dense.argtypes = [c_int32, c_int32, c_int32, c_int64, c_int32, vp, vp, vp, vp, vp, vp]
+    lib.crl_update_traj.argtypes = [P, vp, vp, vp, c_double, vp, vp, vp]
+    lib.crl_forward_pass.argtypes = [P, O, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.crl_solve_workspace_bytes.restype = c_size_t
+    lib.crl_solve_workspace_bytes.argtypes = [P, O]
+    lib.crl_solve.argtypes = [P, O, vp, vp, c_int64, vp, vp, vp, vp, vp, vp, vp, vp, c_size_t, vp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("crl_status_string", "crl_solve_workspace_bytes"):
+            fn.restype = c_int
+
+
+def load():
+    """Load (building first if the in-tree library is missing or stale and nvcc is present)."""
+    global _lib
+    if _lib is None:
+        path = _build.LIB_PATH
+        if _build.is_stale() and _build.find_nvcc() is not None:
+            path = _build.build_native()
+        if not os.path.exists(path):
+            raise RuntimeError("curiousrl_b200: %s not found and cannot be built (no nvcc). "
+                               "There is no CPU fallback for the iLQR path." % path)
+        lib = ctypes.CDLL(path)
+        _declare(lib)
+        if lib.crl_abi_version() != 1:
+            raise RuntimeError("curiousrl_b200: ABI version mismatch in %s" % path)
+        _lib = lib
+    return _lib
+
+
+def check(status: int, what: str = "call"):
+    if status != 0:
+        msg = load().crl_status_string(status).decode()
+        raise RuntimeError("curiousrl_b200 %s failed: %s (status %d)" % (what, msg, status))
+
+
+def model_dims(model_id: int):
+    n, m, p = c_int(), c_int(), c_int()
+    check(load().crl_model_dims(model_id, n, m, p), "crl_model_dims")
+    return n.value, m.value, p.value
+
+
+def model_default_bounds(model_id: int):
+    lo, hi = c_double(), c_double()
+    check(load().crl_model_default_bounds(model_id, lo, hi), "crl_model_default_bounds")
+    return lo.value, hi.value

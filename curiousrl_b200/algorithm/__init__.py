@@ -1,0 +1,1 @@
+from .algo_wrapper import AlgoWrapper

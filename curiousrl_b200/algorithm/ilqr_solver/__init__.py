@@ -1,0 +1,2 @@
+from .device import BatchResult, DeviceModel
+from .solver import iLQRWrapper, iLQRObjectiveFunction, iLQRDynamicModel, BasiciLQR

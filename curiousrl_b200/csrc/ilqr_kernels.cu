@@ -1,0 +1,618 @@
+// CUDA kernels + C ABI of the batched-iLQR path (sm_100a).
+//
+// Mapping: one lane = one trajectory.  The matrices of the Riccati recursion (n <= 8,
+// m <= 3) live in that lane's registers; a warp therefore advances 32 trajectories in
+// lock step and every global access is a 32-lane row of one component (SoA tiles), i.e.
+// one or two full 128-byte lines.  Tensor cores are not used: the contractions are 2x2 ...
+// 8x8 with structural zeros, far below one MMA tile.
+//
+// Kernels
+//   stage kernels (API layout [B][T][..], one thread per trajectory): rollout, cost, derivs,
+//     backward, backward_dense, update_traj, forward_pass - the reference's operator surface,
+//     used for B = 1 compatibility calls and stage-parity tests;
+//   solve_kernel: the product path.  Persistent grid; each lane pulls trajectories from a
+//     global counter, keeps its working set (X_cur, X_new, K, k) in a warp-tile workspace slot
+//     and iterates {backward, multi-alpha line search, accept/stop} until its trajectory
+//     stops, then writes the result and pulls the next one.  No host round trip, no
+//     compaction pass, memory footprint independent of B.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/curiousrl_b200.h"
+#include "ilqr_core.cuh"
+
+namespace crl {
+
+constexpr int kBlock = 128;       // threads per CTA (4 warps)
+constexpr unsigned kFull = 0xffffffffu;
+
+template <class R>
+struct ProblemDev {
+    const R* params;
+    long long params_stride_b;
+    int params_stride_t;
+    long long B;
+    int T;
+    Bounds<R> ub;
+    __device__ ParamRef<R> prm(long long b) const { return ParamRef<R>{params + b * params_stride_b, params_stride_t}; }
+};
+
+// ------------------------------------------------------------------------------ stage kernels
+template <class Mdl, class R>
+__global__ void __launch_bounds__(kBlock) rollout_kernel(ProblemDev<R> pb, const R* x0, const R* u0, long long u0_sb,
+                                                         R* X, double* J) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= pb.B) return;
+    View<R, Mdl::D, 1> Xv{X + b * pb.T * Mdl::D};
+    const double Jb = rollout_open<Mdl, R, 1>(x0 + b * Mdl::N, 1, u0 ? u0 + b * u0_sb : nullptr, Mdl::M, pb.prm(b),
+                                              pb.ub, pb.T, Xv);
+    if (J) J[b] = Jb;
+}
+
+template <class Mdl, class R>
+__global__ void __launch_bounds__(kBlock) cost_kernel(ProblemDev<R> pb, const R* X, double* J) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= pb.B) return;
+    const ParamRef<R> prm = pb.prm(b);
+    const R* Xb = X + b * pb.T * Mdl::D;
+    double acc = 0.0;
+    for (int t = 0; t < pb.T; ++t) {
+        R xu[Mdl::D];
+#pragma unroll
+        for (int i = 0; i < Mdl::D; ++i) xu[i] = Xb[(size_t)t * Mdl::D + i];
+        acc = acc + step_cost<Mdl, R>(xu, prm, t);
+    }
+    J[b] = acc;
+}
+
+template <class Mdl, class R>
+__global__ void __launch_bounds__(kBlock) derivs_kernel(ProblemDev<R> pb, const R* X, R* F, R* c, R* C) {
+    constexpr int N = Mdl::N, D = Mdl::D, P = Mdl::P;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (b, t)
+    if (idx >= pb.B * pb.T) return;
+    const long long b = idx / pb.T;
+    const int t = (int)(idx % pb.T);
+    const ParamRef<R> prm = pb.prm(b);
+    R xu[D], p[P], Fl[N * D], cl[D], Cl[D * D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) xu[i] = X[idx * D + i];
+#pragma unroll
+    for (int i = 0; i < P; ++i) p[i] = prm.get(t, i);
+    derivs_dense<Mdl, R>(xu, p, Fl, cl, Cl);
+    if (F) for (int i = 0; i < N * D; ++i) F[idx * N * D + i] = Fl[i];
+    if (c) for (int i = 0; i < D; ++i) c[idx * D + i] = cl[i];
+    if (C) for (int i = 0; i < D * D; ++i) C[idx * D * D + i] = Cl[i];
+}
+
+template <class Mdl, class R>
+__global__ void __launch_bounds__(kBlock) backward_kernel(ProblemDev<R> pb, const R* X, R* K, R* k) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= pb.B) return;
+    View<R, Mdl::D, 1> Xv{const_cast<R*>(X) + b * pb.T * Mdl::D};
+    View<R, Mdl::M * Mdl::N, 1> Kv{K + b * pb.T * Mdl::M * Mdl::N};
+    View<R, Mdl::M, 1> kv{k + b * pb.T * Mdl::M};
+    backward_fused<Mdl, R, Mdl::N, 1, 1>(Xv, pb.prm(b), pb.T, Kv, kv);
+}
+
+template <int N, int M, class R>
+__global__ void __launch_bounds__(kBlock) backward_dense_kernel(long long B, int T, const R* F, const R* c, const R* C,
+                                                                R* K, R* k) {
+    constexpr int D = N + M;
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    backward_dense<N, M, R>(F + b * T * N * D, c + b * T * D, C + b * T * D * D, T, K + b * T * M * N, k + b * T * M);
+}
+
+template <class Mdl, class R>
+__global__ void __launch_bounds__(kBlock) update_traj_kernel(ProblemDev<R> pb, const R* X, const R* K, const R* k,
+                                                             double alpha, R* Xn, double* Jn) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= pb.B) return;
+    View<R, Mdl::D, 1> Xo{const_cast<R*>(X) + b * pb.T * Mdl::D};
+    View<R, Mdl::D, 1> Xw{Xn + b * pb.T * Mdl::D};
+    View<R, Mdl::M * Mdl::N, 1> Kv{const_cast<R*>(K) + b * pb.T * Mdl::M * Mdl::N};
+    View<R, Mdl::M, 1> kv{const_cast<R*>(k) + b * pb.T * Mdl::M};
+    const double J = rollout_closed<Mdl, R, Mdl::N, 1, 1, 1>(Xo, Kv, kv, (R)alpha, pb.prm(b), pb.ub, pb.T, Xw);
+    if (Jn) Jn[b] = J;
+}
+
+struct OptsDev {
+    int max_iter, check_stop, max_ls, ls_method, stop_method;
+    double criterion, gamma;
+};
+
+template <class Mdl, class R>
+__global__ void __launch_bounds__(kBlock) forward_pass_kernel(ProblemDev<R> pb, OptsDev op, const R* X, const R* K,
+                                                              const R* k, const double* J_last, R* Xn, double* J_new,
+                                                              int* alpha_index, uint8_t* stop) {
+    constexpr int D = Mdl::D;
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= pb.B) return;
+    View<R, D, 1> Xo{const_cast<R*>(X) + b * pb.T * D};
+    View<R, D, 1> Xw{Xn + b * pb.T * D};
+    View<R, Mdl::M * Mdl::N, 1> Kv{const_cast<R*>(K) + b * pb.T * Mdl::M * Mdl::N};
+    View<R, Mdl::M, 1> kv{const_cast<R*>(k) + b * pb.T * Mdl::M};
+    const ParamRef<R> prm = pb.prm(b);
+    const double Jl = J_last[b];
+    double Jn = Jl, alpha = 1.0;
+    int taken = -1;
+    const int tries = (op.ls_method == CRL_LS_NONE) ? 1 : op.max_ls;
+    for (int a = 0; a < tries && taken < 0; ++a) {
+        const double Jt = rollout_closed<Mdl, R, Mdl::N, 1, 1, 1>(Xo, Kv, kv, (R)alpha, prm, pb.ub, pb.T, Xw);
+        alpha = alpha * op.gamma;
+        if (op.ls_method == CRL_LS_NONE || ls_accept(Jt, Jl, op.ls_method == CRL_LS_FEASIBILITY)) {
+            taken = a;
+            Jn = Jt;
+        }
+    }
+    if (taken < 0) {   // no step accepted: the trajectory is returned unchanged (ilqr_wrapper.py:100)
+        for (int i = 0; i < pb.T * D; ++i) Xw.base[i] = Xo.base[i];
+    }
+    J_new[b] = Jn;
+    alpha_index[b] = taken;
+    stop[b] = stop_test(Jn, Jl, op.criterion, op.stop_method == CRL_STOP_RELATIVE) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------ persistent solve
+template <class R>
+struct SolveArgs {
+    ProblemDev<R> pb;
+    OptsDev op;
+    const R* x0;
+    const R* u0;
+    long long u0_sb;
+    const double* J_init;
+    R* X_out;
+    double* J_out;
+    int* iters_out;
+    uint8_t* conv_out;
+    double* J_trace;
+    int8_t* alpha_trace;
+    R* ws;                         // [slots][slot_elems]
+    long long slot_elems;          // reals per warp slot
+    unsigned long long* counter;   // next unassigned trajectory
+};
+
+template <class Mdl>
+__host__ __device__ constexpr long long slot_reals(int T) {
+    return (long long)T * 32 * (2 * Mdl::D + Mdl::M * Mdl::NS + Mdl::M);
+}
+
+template <class Mdl, class R, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) solve_kernel(SolveArgs<R> a) {
+    constexpr int N = Mdl::N, M = Mdl::M, D = Mdl::D, NS = Mdl::NS;
+    const int lane = threadIdx.x & 31;
+    const long long slot = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int T = a.pb.T;
+    R* wsb = a.ws + slot * a.slot_elems + lane;
+    const View<R, D, 32> Xbuf0{wsb}, Xbuf1{wsb + (size_t)T * D * 32};
+    const View<R, M * NS, 32> Kv{wsb + (size_t)2 * T * D * 32};
+    const View<R, M, 32> kv{wsb + (size_t)2 * T * D * 32 + (size_t)T * M * NS * 32};
+
+    int cur = 0;                 // warp-uniform: which X buffer holds the current trajectories
+    bool exhausted = false;      // warp-uniform: the global queue is empty
+    long long traj = -1;         // this lane's trajectory, -1 = idle
+    int it = 0;
+    double J_last = 0.0;
+    ParamRef<R> prm{a.pb.params, 0};
+
+    while (true) {
+        // ---- refill idle lanes from the global queue
+        const unsigned need = __ballot_sync(kFull, traj < 0);
+        if (need != 0u && !exhausted) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(a.counter, (unsigned long long)__popc(need));
+            base = __shfl_sync(kFull, base, 0);
+            if (base + __popc(need) >= (unsigned long long)a.pb.B) exhausted = true;
+            if (traj < 0) {
+                const long long idx = (long long)base + __popc(need & ((1u << lane) - 1u));
+                if (idx < a.pb.B) {
+                    traj = idx;
+                    it = 0;
+                    J_last = a.J_init ? a.J_init[idx] : (double)INFINITY;
+                    prm = a.pb.prm(idx);
+                    const View<R, D, 32> Xc = cur ? Xbuf1 : Xbuf0;
+                    rollout_open<Mdl, R, 32>(a.x0 + idx * N, 1, a.u0 ? a.u0 + idx * a.u0_sb : nullptr, M, prm, a.pb.ub, T,
+                                             Xc);
+                }
+            }
+        }
+        const bool active = traj >= 0;
+        if (!__any_sync(kFull, active)) break;
+
+        const View<R, D, 32> Xc = cur ? Xbuf1 : Xbuf0;
+        const View<R, D, 32> Xn = cur ? Xbuf0 : Xbuf1;
+
+        // ---- backward pass: K, k for every active lane
+        if (active) backward_fused<Mdl, R, NS, 32, 32>(Xc, prm, T, Kv, kv);
+
+        // ---- line search: first improving alpha = 1, g, g^2, ...  (lanes drop out as they accept)
+        bool accepted = false;
+        double J_new = J_last, alpha = 1.0;
+        int taken = -1;
+        const int tries = (a.op.ls_method == CRL_LS_NONE) ? 1 : a.op.max_ls;
+        for (int ls = 0; ls < tries; ++ls) {
+            const bool pending = active && !accepted;
+            if (!__any_sync(kFull, pending)) break;
+            if (pending) {
+                const double Jt = rollout_closed<Mdl, R, NS, 32, 32, 32>(Xc, Kv, kv, (R)alpha, prm, a.pb.ub, T, Xn);
+                if (a.op.ls_method == CRL_LS_NONE || ls_accept(Jt, J_last, a.op.ls_method == CRL_LS_FEASIBILITY)) {
+                    accepted = true;
+                    J_new = Jt;
+                    taken = ls;
+                }
+            }
+            alpha = alpha * a.op.gamma;
+        }
+
+        // ---- stop test, bookkeeping, retirement
+        bool finished = false;
+        if (active) {
+            const bool stop = stop_test(J_new, J_last, a.op.criterion, a.op.stop_method == CRL_STOP_RELATIVE);
+            J_last = J_new;
+            if (a.J_trace) a.J_trace[traj * a.op.max_iter + it] = J_new;
+            if (a.alpha_trace) a.alpha_trace[traj * a.op.max_iter + it] = (int8_t)taken;
+            ++it;
+            finished = (stop && a.op.check_stop) || it >= a.op.max_iter;
+            if (finished) {
+                a.J_out[traj] = J_last;
+                a.iters_out[traj] = it;
+                a.conv_out[traj] = (stop && a.op.check_stop) ? 1 : 0;
+                if (a.X_out) {
+                    const View<R, D, 32> src = accepted ? Xn : Xc;
+                    R* dst = a.X_out + traj * T * D;
+                    for (int t = 0; t < T; ++t) {
+                        const R* row = src.row(t);
+#pragma unroll
+                        for (int i = 0; i < D; ++i) dst[(size_t)t * D + i] = src.ld(row, i);
+                    }
+                }
+            }
+        }
+        // lanes that go on without an accepted step carry their trajectory into the other
+        // buffer so that `cur` can flip for the whole warp
+        const bool carry = active && !finished && !accepted;
+        if (__any_sync(kFull, carry)) {
+            if (carry) {
+                for (int t = 0; t < T; ++t) {
+                    const R* src = Xc.row(t);
+                    R* dst = Xn.row(t);
+#pragma unroll
+                    for (int i = 0; i < D; ++i) Xn.st(dst, i, Xc.ld(src, i));
+                }
+            }
+        }
+        if (finished) traj = -1;
+        cur ^= 1;
+    }
+}
+
+// ------------------------------------------------------------------------------ host side
+static int cuda_status(cudaError_t e) { return e == cudaSuccess ? CRL_OK : CRL_ERR_CUDA - (int)e; }
+
+template <class R>
+static ProblemDev<R> to_dev(const crl_problem_t* p) {
+    ProblemDev<R> d;
+    d.params = (const R*)p->params;
+    d.params_stride_b = p->params_stride_b;
+    d.params_stride_t = p->params_stride_t;
+    d.B = p->batch;
+    d.T = p->horizon;
+    d.ub.lo = (R)p->u_lo;
+    d.ub.hi = (R)p->u_hi;
+    d.ub.active = !(p->u_lo == -INFINITY && p->u_hi == INFINITY);
+    return d;
+}
+
+static OptsDev to_dev(const crl_solver_opts_t* o) {
+    OptsDev d;
+    d.max_iter = o->max_iter;
+    d.check_stop = o->is_check_stop;
+    d.max_ls = o->max_line_search;
+    d.ls_method = o->line_search_method;
+    d.stop_method = o->stopping_method;
+    d.criterion = o->stopping_criterion;
+    d.gamma = o->gamma;
+    return d;
+}
+
+static int check_problem(const crl_problem_t* p) {
+    if (!p) return CRL_ERR_BAD_ARGUMENT;
+    if (p->model < CRL_TWO_LINK || p->model > CRL_ROBOTIC_ARM) return CRL_ERR_UNSUPPORTED_MODEL;
+    if (p->dtype != CRL_F64 && p->dtype != CRL_F32) return CRL_ERR_BAD_ARGUMENT;
+    if (p->batch < 0 || p->horizon < 1) return CRL_ERR_BAD_ARGUMENT;
+    if (p->batch > 0 && !p->params) return CRL_ERR_BAD_ARGUMENT;
+    if (p->params_stride_t != 0 && p->params_stride_t != 2) return CRL_ERR_BAD_ARGUMENT;
+    if (p->params_stride_b < 0) return CRL_ERR_BAD_ARGUMENT;
+    if (!(p->u_lo <= p->u_hi)) return CRL_ERR_BAD_ARGUMENT;
+    return CRL_OK;
+}
+
+static int check_opts(const crl_solver_opts_t* o) {
+    if (!o) return CRL_ERR_BAD_ARGUMENT;
+    if (o->max_iter < 0 || o->max_line_search < 0) return CRL_ERR_BAD_ARGUMENT;
+    if (o->line_search_method < CRL_LS_VANILLA || o->line_search_method > CRL_LS_NONE) return CRL_ERR_BAD_ARGUMENT;
+    if (o->stopping_method < CRL_STOP_RELATIVE || o->stopping_method > CRL_STOP_VANILLA) return CRL_ERR_BAD_ARGUMENT;
+    return CRL_OK;
+}
+
+// Makes the device that owns `ptr` current for the duration of a call (the library links its
+// own CUDA runtime, so it cannot rely on the caller's cudaSetDevice) and rejects host pointers.
+struct DeviceScope {
+    int prev = -1, status = CRL_OK;
+    bool changed = false;
+    explicit DeviceScope(const void* ptr) {
+        cudaPointerAttributes at;
+        cudaError_t e = cudaPointerGetAttributes(&at, ptr);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            status = (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? CRL_ERR_NO_DEVICE : cuda_status(e);
+            return;
+        }
+        if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) {
+            status = CRL_ERR_BAD_ARGUMENT;      // host memory: this library only takes device pointers
+            return;
+        }
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != at.device) {
+            status = cuda_status(cudaSetDevice(at.device));
+            changed = (status == CRL_OK);
+        }
+    }
+    ~DeviceScope() {
+        if (changed) cudaSetDevice(prev);
+    }
+};
+
+static unsigned blocks_for(long long work) { return (unsigned)((work + kBlock - 1) / kBlock); }
+
+// model x dtype dispatch: the body (variadic, may contain commas) sees `Mdl` and `R`
+#define CRL_DISPATCH(model, dtype, ...)                                                  \
+    do {                                                                                 \
+        if ((dtype) == CRL_F64) {                                                        \
+            using R = double;                                                            \
+            switch (model) {                                                             \
+                case CRL_TWO_LINK: { using Mdl = TwoLink; __VA_ARGS__; } break;                 \
+                case CRL_THREE_LINK: { using Mdl = ThreeLink; __VA_ARGS__; } break;             \
+                case CRL_ROBOTIC_ARM: { using Mdl = RoboticArm; __VA_ARGS__; } break;           \
+            }                                                                            \
+        } else {                                                                         \
+            using R = float;                                                             \
+            switch (model) {                                                             \
+                case CRL_TWO_LINK: { using Mdl = TwoLink; __VA_ARGS__; } break;                 \
+                case CRL_THREE_LINK: { using Mdl = ThreeLink; __VA_ARGS__; } break;             \
+                case CRL_ROBOTIC_ARM: { using Mdl = RoboticArm; __VA_ARGS__; } break;           \
+            }                                                                            \
+        }                                                                                \
+    } while (0)
+
+// resident CTAs per SM the solve kernel is compiled for (register budget = 65536 / (MINB * 128))
+template <class R> struct SolveCfg;
+template <> struct SolveCfg<double> { static constexpr int MINB = 2; };
+template <> struct SolveCfg<float> { static constexpr int MINB = 4; };
+
+template <class Mdl, class R>
+static int solve_grid(int requested) {
+    if (requested > 0) return requested;
+    int dev = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel<Mdl, R, SolveCfg<R>::MINB>, kBlock, 0) !=
+        cudaSuccess)
+        return -1;
+    if (per_sm < 1) per_sm = 1;
+    return sms * per_sm;
+}
+
+}  // namespace crl
+
+using namespace crl;
+
+extern "C" {
+
+int crl_abi_version(void) { return CRL_ABI_VERSION; }
+
+const char* crl_status_string(int status) {
+    switch (status) {
+        case CRL_OK: return "ok";
+        case CRL_ERR_BAD_ARGUMENT: return "bad argument";
+        case CRL_ERR_UNSUPPORTED_MODEL: return "unsupported model (no device model compiled for this scenario)";
+        case CRL_ERR_WORKSPACE_TOO_SMALL: return "workspace too small";
+        case CRL_ERR_NO_DEVICE: return "no CUDA device";
+        default: break;
+    }
+    if (status <= CRL_ERR_CUDA) return cudaGetErrorString((cudaError_t)(CRL_ERR_CUDA - status));
+    return "unknown status";
+}
+
+int crl_model_dims(int model, int* n, int* m, int* p) {
+    int N, M, P;
+    switch (model) {
+        case CRL_TWO_LINK: N = TwoLink::N; M = TwoLink::M; P = TwoLink::P; break;
+        case CRL_THREE_LINK: N = ThreeLink::N; M = ThreeLink::M; P = ThreeLink::P; break;
+        case CRL_ROBOTIC_ARM: N = RoboticArm::N; M = RoboticArm::M; P = RoboticArm::P; break;
+        default: return CRL_ERR_UNSUPPORTED_MODEL;
+    }
+    if (n) *n = N;
+    if (m) *m = M;
+    if (p) *p = P;
+    return CRL_OK;
+}
+
+int crl_model_default_bounds(int model, double* u_lo, double* u_hi) {
+    double lo, hi;
+    switch (model) {
+        case CRL_TWO_LINK: lo = TwoLink::u_lo(0); hi = TwoLink::u_hi(0); break;
+        case CRL_THREE_LINK: lo = ThreeLink::u_lo(0); hi = ThreeLink::u_hi(0); break;
+        case CRL_ROBOTIC_ARM: lo = RoboticArm::u_lo(0); hi = RoboticArm::u_hi(0); break;
+        default: return CRL_ERR_UNSUPPORTED_MODEL;
+    }
+    if (u_lo) *u_lo = lo;
+    if (u_hi) *u_hi = hi;
+    return CRL_OK;
+}
+
+int crl_rollout(const crl_problem_t* prob, const void* x0, const void* u0, int64_t u0_stride_b, void* X, double* J,
+                crl_stream_t stream) {
+    int st = check_problem(prob);
+    if (st) return st;
+    if (prob->batch == 0) return CRL_OK;
+    if (!x0 || !X) return CRL_ERR_BAD_ARGUMENT;
+    DeviceScope scope(x0);
+    if (scope.status) return scope.status;
+    cudaStream_t s = (cudaStream_t)stream;
+    CRL_DISPATCH(prob->model, prob->dtype, (rollout_kernel<Mdl, R><<<blocks_for(prob->batch), kBlock, 0, s>>>(
+                                               to_dev<R>(prob), (const R*)x0, (const R*)u0, u0_stride_b, (R*)X, J)));
+    return cuda_status(cudaGetLastError());
+}
+
+int crl_cost(const crl_problem_t* prob, const void* X, double* J, crl_stream_t stream) {
+    int st = check_problem(prob);
+    if (st) return st;
+    if (prob->batch == 0) return CRL_OK;
+    if (!X || !J) return CRL_ERR_BAD_ARGUMENT;
+    DeviceScope scope(X);
+    if (scope.status) return scope.status;
+    cudaStream_t s = (cudaStream_t)stream;
+    CRL_DISPATCH(prob->model, prob->dtype,
+                 (cost_kernel<Mdl, R><<<blocks_for(prob->batch), kBlock, 0, s>>>(to_dev<R>(prob), (const R*)X, J)));
+    return cuda_status(cudaGetLastError());
+}
+
+int crl_derivs(const crl_problem_t* prob, const void* X, void* F, void* c, void* C, crl_stream_t stream) {
+    int st = check_problem(prob);
+    if (st) return st;
+    if (prob->batch == 0) return CRL_OK;
+    if (!X) return CRL_ERR_BAD_ARGUMENT;
+    DeviceScope scope(X);
+    if (scope.status) return scope.status;
+    cudaStream_t s = (cudaStream_t)stream;
+    CRL_DISPATCH(prob->model, prob->dtype,
+                 (derivs_kernel<Mdl, R><<<blocks_for(prob->batch * prob->horizon), kBlock, 0, s>>>(
+                     to_dev<R>(prob), (const R*)X, (R*)F, (R*)c, (R*)C)));
+    return cuda_status(cudaGetLastError());
+}
+
+int crl_backward(const crl_problem_t* prob, const void* X, void* K, void* k, crl_stream_t stream) {
+    int st = check_problem(prob);
+    if (st) return st;
+    if (prob->batch == 0) return CRL_OK;
+    if (!X || !K || !k) return CRL_ERR_BAD_ARGUMENT;
+    DeviceScope scope(X);
+    if (scope.status) return scope.status;
+    cudaStream_t s = (cudaStream_t)stream;
+    CRL_DISPATCH(prob->model, prob->dtype, (backward_kernel<Mdl, R><<<blocks_for(prob->batch), kBlock, 0, s>>>(
+                                               to_dev<R>(prob), (const R*)X, (R*)K, (R*)k)));
+    return cuda_status(cudaGetLastError());
+}
+
+int crl_backward_dense(int32_t n, int32_t m, int32_t dtype, int64_t batch, int32_t horizon, const void* F, const void* c,
+                       const void* C, void* K, void* k, crl_stream_t stream) {
+    if (batch < 0 || horizon < 1 || (dtype != CRL_F64 && dtype != CRL_F32)) return CRL_ERR_BAD_ARGUMENT;
+    if (!((n == 6 && m == 2) || (n == 8 && m == 3))) return CRL_ERR_UNSUPPORTED_MODEL;
+    if (batch == 0) return CRL_OK;
+    if (!F || !c || !C || !K || !k) return CRL_ERR_BAD_ARGUMENT;
+    DeviceScope scope(F);
+    if (scope.status) return scope.status;
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned g = blocks_for(batch);
+#define CRL_BD(NN, MM, RR)                                                                                           \
+    backward_dense_kernel<NN, MM, RR><<<g, kBlock, 0, s>>>(batch, horizon, (const RR*)F, (const RR*)c, (const RR*)C, \
+                                                           (RR*)K, (RR*)k)
+    if (n == 6 && dtype == CRL_F64) CRL_BD(6, 2, double);
+    else if (n == 6) CRL_BD(6, 2, float);
+    else if (dtype == CRL_F64) CRL_BD(8, 3, double);
+    else CRL_BD(8, 3, float);
+#undef CRL_BD
+    return cuda_status(cudaGetLastError());
+}
+
+int crl_update_traj(const crl_problem_t* prob, const void* X, const void* K, const void* k, double alpha, void* X_new,
+                    double* J_new, crl_stream_t stream) {
+    int st = check_problem(prob);
+    if (st) return st;
+    if (prob->batch == 0) return CRL_OK;
+    if (!X || !K || !k || !X_new) return CRL_ERR_BAD_ARGUMENT;
+    DeviceScope scope(X);
+    if (scope.status) return scope.status;
+    cudaStream_t s = (cudaStream_t)stream;
+    CRL_DISPATCH(prob->model, prob->dtype,
+                 (update_traj_kernel<Mdl, R><<<blocks_for(prob->batch), kBlock, 0, s>>>(
+                     to_dev<R>(prob), (const R*)X, (const R*)K, (const R*)k, alpha, (R*)X_new, J_new)));
+    return cuda_status(cudaGetLastError());
+}
+
+int crl_forward_pass(const crl_problem_t* prob, const crl_solver_opts_t* opts, const void* X, const void* K,
+                     const void* k, const double* J_last, void* X_new, double* J_new, int32_t* alpha_index,
+                     uint8_t* stop, crl_stream_t stream) {
+    int st = check_problem(prob);
+    if (st) return st;
+    st = check_opts(opts);
+    if (st) return st;
+    if (prob->batch == 0) return CRL_OK;
+    if (!X || !K || !k || !J_last || !X_new || !J_new || !alpha_index || !stop) return CRL_ERR_BAD_ARGUMENT;
+    DeviceScope scope(X);
+    if (scope.status) return scope.status;
+    cudaStream_t s = (cudaStream_t)stream;
+    CRL_DISPATCH(prob->model, prob->dtype,
+                 (forward_pass_kernel<Mdl, R><<<blocks_for(prob->batch), kBlock, 0, s>>>(
+                     to_dev<R>(prob), to_dev(opts), (const R*)X, (const R*)K, (const R*)k, J_last, (R*)X_new, J_new,
+                     alpha_index, stop)));
+    return cuda_status(cudaGetLastError());
+}
+
+size_t crl_solve_workspace_bytes(const crl_problem_t* prob, const crl_solver_opts_t* opts) {
+    if (check_problem(prob) || check_opts(opts)) return 0;
+    long long reals = 0;
+    int grid = 0;
+    CRL_DISPATCH(prob->model, prob->dtype, (reals = slot_reals<Mdl>(prob->horizon), grid = solve_grid<Mdl, R>(opts->grid_blocks)));
+    if (grid <= 0) return 0;
+    const size_t elem = prob->dtype == CRL_F64 ? 8 : 4;
+    const size_t slots = (size_t)grid * (kBlock / 32);
+    return 256 + slots * (size_t)reals * elem;     // first 256 bytes: the work counter
+}
+
+int crl_solve(const crl_problem_t* prob, const crl_solver_opts_t* opts, const void* x0, const void* u0,
+              int64_t u0_stride_b, const double* J_init, void* X, double* J, int32_t* iters, uint8_t* converged,
+              double* J_trace, int8_t* alpha_trace, void* workspace, size_t workspace_bytes, crl_stream_t stream) {
+    int st = check_problem(prob);
+    if (st) return st;
+    st = check_opts(opts);
+    if (st) return st;
+    if (prob->batch == 0) return CRL_OK;
+    if (!x0 || !J || !iters || !converged || !workspace) return CRL_ERR_BAD_ARGUMENT;
+    if (opts->max_iter < 1) return CRL_ERR_BAD_ARGUMENT;
+    if (((uintptr_t)workspace & 255u) != 0) return CRL_ERR_BAD_ARGUMENT;
+    const size_t need = crl_solve_workspace_bytes(prob, opts);
+    if (need == 0) return CRL_ERR_NO_DEVICE;
+    if (workspace_bytes < need) return CRL_ERR_WORKSPACE_TOO_SMALL;
+    DeviceScope scope(x0);
+    if (scope.status) return scope.status;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(workspace, 0, 256, s);
+    if (e != cudaSuccess) return cuda_status(e);
+    CRL_DISPATCH(prob->model, prob->dtype, {
+        SolveArgs<R> a;
+        a.pb = to_dev<R>(prob);
+        a.op = to_dev(opts);
+        a.x0 = (const R*)x0;
+        a.u0 = (const R*)u0;
+        a.u0_sb = u0_stride_b;
+        a.J_init = J_init;
+        a.X_out = (R*)X;
+        a.J_out = J;
+        a.iters_out = iters;
+        a.conv_out = converged;
+        a.J_trace = J_trace;
+        a.alpha_trace = alpha_trace;
+        a.counter = (unsigned long long*)workspace;
+        a.ws = (R*)((char*)workspace + 256);
+        a.slot_elems = slot_reals<Mdl>(prob->horizon);
+        const int grid = solve_grid<Mdl, R>(opts->grid_blocks);
+        solve_kernel<Mdl, R, SolveCfg<R>::MINB><<<grid, kBlock, 0, s>>>(a);
+    });
+    return cuda_status(cudaGetLastError());
+}
+
+}  // extern "C"

@@ -1,0 +1,239 @@
+// Device models of the three arm scenarios: dynamics, analytic Jacobians, tracking cost.
+//
+// Hand-written from the scenario formulas (reference files, relative to
+// /root/reference/CuriousRL/scenario/dynamic_model/):
+//   TwoLink    two_link_planar_manipulator.py:27-44     n=6 m=2
+//   ThreeLink  three_link_planar_manipulator.py:30-59   n=8 m=3
+//   RoboticArm robotic_arm_tracking.py:28-66            n=6 m=2
+// Expression forms (operation order, printed constants) follow what the reference's
+// sympy -> lambdify pipeline evaluates, so results agree with it to rounding.
+//
+// Shared structure exploited by the Riccati kernel (ilqr_core.cuh).  The state splits into
+// NS "dynamic" entries s (joint angles/velocities) and NO = 2 "output" entries y (the
+// end-effector position) that are functions of the previous s only and never feed back:
+//
+//        | A(s,u)   0   B(s) |   rows: s'          A: NS x NS, B: NS x M
+//    F = |                   |
+//        | G(s)     0   0    |   rows: y'          G: NO x NS
+//
+// Every entry of A, B, G has a compile-time kind: structural zero, one, constant, or
+// variable.  Multiplying by structural zeros/ones is exact, so pruning them changes nothing
+// but the operation count.  The cost is  sum_i w_i (xu_i - r_i)^2  with the target on y.
+#pragma once
+
+#include "ilqr_common.cuh"
+
+namespace crl {
+
+enum Kind : int { KZ = 0, K1 = 1, KC = 2, KV = 3 };
+
+// Euler-integrated joint: theta' = theta + h*omega ; omega' = omega + h*(acceleration)
+constexpr double kH = 0.01;
+
+// -----------------------------------------------------------------------------------------
+// Kinematic chains (TwoLink J=2, ThreeLink J=3): accelerations are the controls.
+template <int J>
+struct KinematicArm {
+    static constexpr int NS = 2 * J, NO = 2, N = NS + NO, M = J, D = N + M, P = 2;
+
+    CRL_HD static constexpr int akind(int i, int j) { return i == j ? K1 : ((i % 2 == 0 && j == i + 1) ? KC : KZ); }
+    CRL_HD static constexpr double aconst(int, int) { return kH; }
+    CRL_HD static constexpr int bkind(int i, int a) { return (i % 2 == 1 && a == i / 2) ? KC : KZ; }
+    CRL_HD static constexpr double bconst(int, int) { return kH; }
+    CRL_HD static constexpr int gkind(int, int j) { return (j % 2 == 0) ? KV : KZ; }
+
+    CRL_HD static constexpr double link(int j) { return j == 0 ? 1.0 : 2.0; }       // l1 = 1, l2 = l3 = 2
+    CRL_HD static constexpr double weight(int i) {                                  // cost diag
+        return i < NS ? ((i % 2) ? 10.0 : 0.0) : (i < N ? 1e4 : 1.0);
+    }
+    CRL_HD static constexpr double u_lo(int) { return -100.0; }
+    CRL_HD static constexpr double u_hi(int) { return 100.0; }
+
+    // x_{t+1} = f(x_t, u_t); xu = (s, y, u)
+    template <class R>
+    CRL_HD static void step(const R* xu, R* xn) {
+        CRL_UNROLL for (int j = 0; j < J; ++j) {
+            xn[2 * j] = xu[2 * j] + R(kH) * xu[2 * j + 1];
+            xn[2 * j + 1] = xu[2 * j + 1] + R(kH) * xu[N + j];
+        }
+        R ang = xu[0], ex, ey, s, c;
+        sincos_(ang, &s, &c);
+        ex = s; ey = c;                                      // l1 = 1: sympy prints sin(x0), not 1*sin(x0)
+        CRL_UNROLL for (int j = 1; j < J; ++j) {
+            ang = ang + xu[2 * j];
+            sincos_(ang, &s, &c);
+            ex = ex + R(link(j)) * s;
+            ey = ey + R(link(j)) * c;
+        }
+        xn[NS] = ex;
+        xn[NS + 1] = ey;
+    }
+
+    // Variable Jacobian entries: G[0][2i] = sum_{j>=i} l_j cos(a_j), G[1][2i] = -sum_{j>=i} l_j sin(a_j)
+    template <class R>
+    CRL_HD static void jac(const R* xu, R (*A)[NS], R (*B)[M], R (*G)[NS]) {
+        (void)A; (void)B;
+        R sn[J], cs[J];
+        R ang = xu[0];
+        sincos_(ang, &sn[0], &cs[0]);
+        CRL_UNROLL for (int j = 1; j < J; ++j) {
+            ang = ang + xu[2 * j];
+            sincos_(ang, &sn[j], &cs[j]);
+        }
+        CRL_UNROLL for (int i = 0; i < J; ++i) {
+            // left-to-right sums as printed: cos(a_i)*l_i + l_{i+1} cos(a_{i+1}) + ...
+            R gc = (i == 0) ? cs[0] : R(link(i)) * cs[i];
+            R gs = (i == 0) ? -sn[0] : -(R(link(i)) * sn[i]);
+            CRL_UNROLL for (int j = i + 1; j < J; ++j) {
+                gc = gc + R(link(j)) * cs[j];
+                gs = gs - R(link(j)) * sn[j];
+            }
+            G[0][2 * i] = gc;
+            G[1][2 * i] = gs;
+        }
+    }
+};
+
+struct TwoLink : KinematicArm<2> {
+    static constexpr int ID = 0;
+    // 10*x1^2 + 10*x3^2 + 1*x6^2 + 1*x7^2 + (-1e4 p0 + 1e4 x4)(-p0 + x4) + (-1e4 p1 + 1e4 x5)(-p1 + x5)
+    CRL_HD static double cost(const double* x, const double* p) {
+        double J = 10.0 * (x[1] * x[1]);
+        J = J + 10.0 * (x[3] * x[3]);
+        J = J + 1.0 * (x[6] * x[6]);
+        J = J + 1.0 * (x[7] * x[7]);
+        J = J + (-10000.0 * p[0] + 10000.0 * x[4]) * (-p[0] + x[4]);
+        J = J + (-10000.0 * p[1] + 10000.0 * x[5]) * (-p[1] + x[5]);
+        return J;
+    }
+};
+
+struct ThreeLink : KinematicArm<3> {
+    static constexpr int ID = 1;
+    // term order as printed by sympy: x1, x10, x3, x5, x8, x9, then the two target terms
+    CRL_HD static double cost(const double* x, const double* p) {
+        double J = 10.0 * (x[1] * x[1]);
+        J = J + 1.0 * (x[10] * x[10]);
+        J = J + 10.0 * (x[3] * x[3]);
+        J = J + 10.0 * (x[5] * x[5]);
+        J = J + 1.0 * (x[8] * x[8]);
+        J = J + 1.0 * (x[9] * x[9]);
+        J = J + (-10000.0 * p[0] + 10000.0 * x[6]) * (-p[0] + x[6]);
+        J = J + (-10000.0 * p[1] + 10000.0 * x[7]) * (-p[1] + x[7]);
+        return J;
+    }
+};
+
+// -----------------------------------------------------------------------------------------
+// Rigid two-link arm with gravity.  delta = th1 - th2, c = cos(delta), s = sin(delta),
+//   den = 4 c^2 - 56/9 (= -det H),  R1 = tau1 - 2 w2^2 s + 24.5 sin th1,  R2 = tau2 + 2 w1^2 s + 19.6 sin th2
+//   h*ddth1 = (-k1 R1 + 0.02 c R2) / den ,  h*ddth2 = (0.02 c R1 - k2 R2) / den
+// with the constants exactly as the reference's generated code prints them.
+struct RoboticArm {
+    static constexpr int ID = 2;
+    static constexpr int NS = 4, NO = 2, N = 6, M = 2, D = 8, P = 2;
+    static constexpr double k1 = 0.0266666666666667, k2 = 0.0233333333333333, kden = 6.22222222222222;
+
+    CRL_HD static constexpr int akind(int i, int j) {
+        return (i % 2 == 1) ? KV : (i == j ? K1 : (j == i + 1 ? KC : KZ));
+    }
+    CRL_HD static constexpr double aconst(int, int) { return kH; }
+    CRL_HD static constexpr int bkind(int i, int) { return (i % 2 == 1) ? KV : KZ; }
+    CRL_HD static constexpr double bconst(int, int) { return 0.0; }
+    CRL_HD static constexpr int gkind(int, int j) { return (j % 2 == 0) ? KV : KZ; }
+    CRL_HD static constexpr double weight(int i) { return i < NS ? ((i % 2) ? 10.0 : 0.0) : (i < N ? 1e4 : 0.01); }
+    // is_with_constraints=True (the default, robotic_arm_tracking.py:59-62); the unconstrained
+    // variant is served by passing infinite bounds at run time (see SolveParams::u_lo/u_hi).
+    CRL_HD static constexpr double u_lo(int) { return -500.0; }
+    CRL_HD static constexpr double u_hi(int) { return 500.0; }
+
+    template <class R>
+    struct Terms { R s, c, s1, c1, s2, c2, id, R1, R2, a1, a2; };
+
+    template <class R>
+    CRL_HD static void terms(const R* xu, Terms<R>& t) {
+        sincos_(xu[0] - xu[2], &t.s, &t.c);
+        sincos_(xu[0], &t.s1, &t.c1);
+        sincos_(xu[2], &t.s2, &t.c2);
+        R den = R(4.0) * (t.c * t.c) - R(kden);
+        t.id = R(1.0) / den;
+        t.R1 = xu[6] + (R(-2.0) * (xu[3] * xu[3]) * t.s + R(24.5) * t.s1);
+        t.R2 = xu[7] + (R(2.0) * (xu[1] * xu[1]) * t.s + R(19.6) * t.s2);
+        R hc = R(0.02) * t.c;
+        t.a1 = (hc * t.R2 - R(k1) * t.R1) * t.id;
+        t.a2 = (hc * t.R1 - R(k2) * t.R2) * t.id;
+    }
+
+    template <class R>
+    CRL_HD static void step(const R* xu, R* xn) {
+        Terms<R> t;
+        terms(xu, t);
+        xn[0] = xu[0] + R(kH) * xu[1];
+        xn[1] = xu[1] + t.a1;
+        xn[2] = xu[2] + R(kH) * xu[3];
+        xn[3] = xu[3] + t.a2;
+        xn[4] = t.s1 + R(2.0) * t.s2;
+        xn[5] = t.c1 + R(2.0) * t.c2;
+    }
+
+    template <class R>
+    CRL_HD static void jac(const R* xu, R (*A)[NS], R (*B)[M], R (*G)[NS]) {
+        Terms<R> t;
+        terms(xu, t);
+        const R w1 = xu[1], w2 = xu[3], s = t.s, c = t.c, id = t.id;
+        const R hc = R(0.02) * c, hs = R(0.02) * s;
+        // d den / d th1 = -8 c s ; d den / d th2 = +8 c s
+        const R dden = R(-8.0) * (c * s);
+        // partials of R1, R2
+        const R w2sq2c = R(2.0) * (w2 * w2) * c, w1sq2c = R(2.0) * (w1 * w1) * c;
+        const R dR1_0 = R(24.5) * t.c1 - w2sq2c, dR1_2 = w2sq2c, dR1_3 = R(-4.0) * (w2 * s);
+        const R dR2_0 = w1sq2c, dR2_2 = R(19.6) * t.c2 - w1sq2c, dR2_1 = R(4.0) * (w1 * s);
+        // N1 = -k1 R1 + 0.02 c R2 ; N2 = 0.02 c R1 - k2 R2 ; a = N / den ; da = (dN - a dden) / den
+        //   d c / d th1 = -s ; d c / d th2 = +s
+        const R dN1_0 = (hc * dR2_0 - hs * t.R2) - R(k1) * dR1_0;
+        const R dN1_2 = (hc * dR2_2 + hs * t.R2) - R(k1) * dR1_2;
+        const R dN2_0 = (hc * dR1_0 - hs * t.R1) - R(k2) * dR2_0;
+        const R dN2_2 = (hc * dR1_2 + hs * t.R1) - R(k2) * dR2_2;
+        A[1][0] = (dN1_0 - t.a1 * dden) * id;
+        A[1][1] = R(1.0) + (hc * dR2_1) * id;
+        A[1][2] = (dN1_2 + t.a1 * dden) * id;
+        A[1][3] = (R(-k1) * dR1_3) * id;
+        A[3][0] = (dN2_0 - t.a2 * dden) * id;
+        A[3][1] = (R(-k2) * dR2_1) * id;
+        A[3][2] = (dN2_2 + t.a2 * dden) * id;
+        A[3][3] = R(1.0) + (hc * dR1_3) * id;
+        B[1][0] = R(-k1) * id;
+        B[1][1] = hc * id;
+        B[3][0] = hc * id;
+        B[3][1] = R(-k2) * id;
+        G[0][0] = t.c1;
+        G[0][2] = R(2.0) * t.c2;
+        G[1][0] = -t.s1;
+        G[1][2] = R(-2.0) * t.s2;
+    }
+
+    CRL_HD static double cost(const double* x, const double* p) {
+        double J = 10.0 * (x[1] * x[1]);
+        J = J + 10.0 * (x[3] * x[3]);
+        J = J + 0.01 * (x[6] * x[6]);
+        J = J + 0.01 * (x[7] * x[7]);
+        J = J + (-10000.0 * p[0] + 10000.0 * x[4]) * (-p[0] + x[4]);
+        J = J + (-10000.0 * p[1] + 10000.0 * x[5]) * (-p[1] + x[5]);
+        return J;
+    }
+};
+
+// ---- cost derivatives shared by all three (diagonal quadratic tracking cost) -------------
+// grad_i = 2 w_i x_i                       for untargeted entries (printed as 20.0*x, 2.0*x, 0.02*x, or 0)
+// grad_i = -2 w_i p + 2 w_i x_i            for the two end-effector entries (printed -20000.0*p0 + 20000.0*x)
+// hess_ii = 2 w_i + 1e-100                 (ilqr_obj_fun.py:51: "+1e-100*eye" keeps every entry float)
+template <class Mdl, class R>
+CRL_HD R cost_grad(int i, R xi, const R* p) {
+    const R w2 = R(2.0 * Mdl::weight(i));
+    if (i >= Mdl::NS && i < Mdl::N) return (-w2) * p[i - Mdl::NS] + w2 * xi;
+    return (Mdl::weight(i) == 0.0) ? R(0.0) : w2 * xi;
+}
+template <class Mdl>
+CRL_HD constexpr double cost_hess(int i) { return 2.0 * Mdl::weight(i) + 1e-100; }
+
+}  // namespace crl

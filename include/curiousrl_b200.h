@@ -1,0 +1,137 @@
+/*
+ * curiousrl_b200 - C ABI of the B200 batched-iLQR path (libcuriousrl_b200.so).
+ *
+ * Drop-in boundary for the hot path of cheng-zilong/CuriousRL.  The reference has no native
+ * code; its "operator interface" for this path is the set of Python methods the solver looks
+ * up through `self` (paths relative to /root/reference/CuriousRL/algorithm/ilqr_solver/).
+ * Each entry point below names the reference method(s) it replaces.  Python binds these with
+ * ctypes (curiousrl_b200/_native.py); INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host; arrays are dense,
+ *    row-major, element type given by `dtype` (J / traces are always double);
+ *  - shapes use B = batch, T = horizon, n/m/p = state/action/parameter sizes of the model,
+ *    d = n + m;
+ *  - no allocation, no global state, no exceptions: work is enqueued on `stream`
+ *    (a cudaStream_t, 0 = default stream) and the call returns a status at once;
+ *  - status 0 = ok; < 0 = error (crl_status_string()); NaN/Inf in data are not errors, they
+ *    flow through comparisons exactly like the reference's float64 code.
+ */
+#ifndef CURIOUSRL_B200_H
+#define CURIOUSRL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRL_ABI_VERSION 1
+
+typedef void* crl_stream_t; /* cudaStream_t */
+
+enum crl_model {              /* scenario.name -> precompiled device model                     */
+    CRL_TWO_LINK = 0,         /* TwoLinkPlanarManipulator   two_link_planar_manipulator.py:14  */
+    CRL_THREE_LINK = 1,       /* ThreeLinkPlanarManipulator three_link_planar_manipulator.py:15 */
+    CRL_ROBOTIC_ARM = 2       /* RoboticArmTracking         robotic_arm_tracking.py:15         */
+};
+enum crl_dtype { CRL_F64 = 0, CRL_F32 = 1 };
+enum crl_line_search { CRL_LS_VANILLA = 0, CRL_LS_FEASIBILITY = 1, CRL_LS_NONE = 2 }; /* ilqr_wrapper.py:74-146 */
+enum crl_stopping { CRL_STOP_RELATIVE = 0, CRL_STOP_VANILLA = 1 };                    /* ilqr_wrapper.py:148-174 */
+
+enum crl_status {
+    CRL_OK = 0,
+    CRL_ERR_BAD_ARGUMENT = -1,
+    CRL_ERR_UNSUPPORTED_MODEL = -2,
+    CRL_ERR_WORKSPACE_TOO_SMALL = -3,
+    CRL_ERR_NO_DEVICE = -4,
+    CRL_ERR_CUDA = -1000      /* -(1000 + cudaError_t) */
+};
+
+/* One batch of problems: which model, how many trajectories, the per-step cost parameters
+ * (`add_param` of the reference, ilqr_obj_fun.py:43-52) and the action box (`constr`).   */
+typedef struct crl_problem {
+    int32_t model;            /* enum crl_model                                               */
+    int32_t dtype;            /* enum crl_dtype                                               */
+    int64_t batch;            /* B >= 0                                                       */
+    int32_t horizon;          /* T >= 1                                                       */
+    int32_t params_stride_t;  /* elements between time steps of `params`: p, or 0 = constant  */
+    int64_t params_stride_b;  /* elements between trajectories of `params` (0 = shared)       */
+    const void* params;       /* [B][T][p] (or broadcast per the strides)                     */
+    double u_lo, u_hi;        /* action bounds, same for every action; +-inf = unconstrained  */
+} crl_problem_t;
+
+/* BasiciLQR constructor arguments (basic_ilqr.py:13-20).                                      */
+typedef struct crl_solver_opts {
+    int32_t max_iter;
+    int32_t is_check_stop;
+    double stopping_criterion;
+    int32_t max_line_search;
+    double gamma;
+    int32_t line_search_method; /* enum crl_line_search */
+    int32_t stopping_method;    /* enum crl_stopping    */
+    int32_t grid_blocks;        /* 0 = auto: resident CTAs per SM x SM count                   */
+    int32_t reserved;
+} crl_solver_opts_t;
+
+int crl_abi_version(void);
+const char* crl_status_string(int status);
+/* n, m, p of a model; CRL_ERR_UNSUPPORTED_MODEL for anything else (no fallback).               */
+int crl_model_dims(int model, int* n, int* m, int* p);
+/* Default action box of the scenario class (u in [-100,100] / [-500,500]).                      */
+int crl_model_default_bounds(int model, double* u_lo, double* u_hi);
+
+/* iLQRDynamicModel.eval_traj + iLQRObjectiveFunction.eval_obj_fun
+ * (ilqr_dynamic_model.py:39-54,96-109; ilqr_obj_fun.py:54-62,86-95).
+ * x0 [B][n]; u0 [T][m] (u0_stride_b = 0), [B][T][m] (u0_stride_b = T*m) or NULL = zeros;
+ * out: X [B][T][d], J [B] (NULL to skip).                                                       */
+int crl_rollout(const crl_problem_t* prob, const void* x0, const void* u0, int64_t u0_stride_b,
+                void* X, double* J, crl_stream_t stream);
+
+/* eval_obj_fun alone: J [B] of stored trajectories X [B][T][d].                                 */
+int crl_cost(const crl_problem_t* prob, const void* X, double* J, crl_stream_t stream);
+
+/* eval_grad_dynamic_model / eval_grad_obj_fun / eval_hessian_obj_fun
+ * (ilqr_dynamic_model.py:73-81,136-147; ilqr_obj_fun.py:64-84,97-119).
+ * out: F [B][T][n][d], c [B][T][d], C [B][T][d][d]; any may be NULL.                           */
+int crl_derivs(const crl_problem_t* prob, const void* X, void* F, void* c, void* C, crl_stream_t stream);
+
+/* iLQRWrapper.backward_pass with the derivatives recomputed on chip from X
+ * (ilqr_wrapper.py:216-256).  out: K [B][T][m][n], k [B][T][m].                                 */
+int crl_backward(const crl_problem_t* prob, const void* X, void* K, void* k, crl_stream_t stream);
+
+/* iLQRWrapper.backward_pass(C, c, F) on caller-supplied dense matrices (same file:lines);
+ * (n, m) must be one of the supported model shapes.  F [B][T][n][d], c [B][T][d], C [B][T][d][d]. */
+int crl_backward_dense(int32_t n, int32_t m, int32_t dtype, int64_t batch, int32_t horizon,
+                       const void* F, const void* c, const void* C, void* K, void* k, crl_stream_t stream);
+
+/* iLQRDynamicModel.update_traj + eval_obj_fun for one step size per call
+ * (ilqr_dynamic_model.py:56-71,111-134).  out: X_new [B][T][d], J_new [B] (NULL to skip).       */
+int crl_update_traj(const crl_problem_t* prob, const void* X, const void* K, const void* k, double alpha,
+                    void* X_new, double* J_new, crl_stream_t stream);
+
+/* iLQRWrapper.forward_pass without the derivative re-evaluation: line search + stopping test
+ * (ilqr_wrapper.py:74-214).  in: J_last [B]; out: X_new [B][T][d] (the old trajectory when no
+ * step is accepted), J_new [B], alpha_index [B] (-1 = none accepted), stop [B] (0/1).            */
+int crl_forward_pass(const crl_problem_t* prob, const crl_solver_opts_t* opts, const void* X, const void* K,
+                     const void* k, const double* J_last, void* X_new, double* J_new, int32_t* alpha_index,
+                     uint8_t* stop, crl_stream_t stream);
+
+/* BasiciLQR.solve for the whole batch in one persistent kernel (basic_ilqr.py:68-97).
+ *  in : x0 [B][n]; u0 as in crl_rollout; J_init [B] or NULL (= +inf, i.e. set_obj_fun_value(inf));
+ *  out: X [B][T][d] final trajectories (NULL to skip), J [B], iters [B],
+ *       converged [B] (1 = stopped by the criterion, 0 = ran max_iter),
+ *       J_trace [B][max_iter] / alpha_trace [B][max_iter] per-iteration cost and accepted step
+ *       index (-1 = rejected; unused slots untouched) - both may be NULL;
+ *  workspace: at least crl_solve_workspace_bytes() bytes, 256-byte aligned.                     */
+size_t crl_solve_workspace_bytes(const crl_problem_t* prob, const crl_solver_opts_t* opts);
+int crl_solve(const crl_problem_t* prob, const crl_solver_opts_t* opts, const void* x0, const void* u0,
+              int64_t u0_stride_b, const double* J_init, void* X, double* J, int32_t* iters,
+              uint8_t* converged, double* J_trace, int8_t* alpha_trace, void* workspace,
+              size_t workspace_bytes, crl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CURIOUSRL_B200_H */

@@ -1,0 +1,200 @@
+"""End-to-end parity of the persistent solve kernel (through the C ABI) with the reference.
+
+* default problems and seeded batches of Two/ThreeLink: same iteration count, same accepted
+  step sequence, final cost and trajectory <= 1e-9 relative (north_star FP64 bar) on problems
+  the reference itself solves reproducibly under 1e-15 noise;
+* RoboticArm: noise-envelope protocol;
+* FP32: final cost <= 1e-4 relative on noise-stable problems;
+* size-independent properties at the benchmark's batch size.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_scenario
+
+pytestmark = pytest.mark.gpu
+
+
+def make_algo(model, T, **kw):
+    from curiousrl_b200.algorithm.ilqr_solver import BasiciLQR
+    from curiousrl_b200 import logger
+    logger.set_level(45)
+    kw.setdefault("max_line_search", 10)
+    return BasiciLQR(**kw).init(make_scenario(model, T))
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(1e-300, np.abs(b).max()))
+
+
+def stable_mask(g, tol=1e-9):
+    """Problems whose reference solution is reproducible under 1e-15 perturbation of K, k."""
+    it_ok = np.all(g["noise_iters"] == g["batch_iters"][:, None], axis=1)
+    J_ok = np.all(np.abs(g["noise_J"] - g["batch_J"][:, None]) <= tol * np.abs(g["batch_J"][:, None]), axis=1)
+    X_ok = np.all(g["noise_Xerr"] <= tol, axis=1)
+    return it_ok & J_ok & X_ok
+
+
+@pytest.mark.parametrize("tag", ["TwoLink_T100", "ThreeLink_T100", "ThreeLink_T30"])
+def test_default_problem(golden, tag):
+    g = golden(tag)
+    algo = make_algo(str(g["model"]), int(g["T"]))
+    res = algo.solve_batch(g["default_x0"][None], g["default_target"][None], trace=True).to_host()
+    n = int(g["default_iters"])
+    assert int(res.iterations[0]) == n and int(res.converged[0]) == 1
+    assert np.array_equal(res.alpha_trace[0, :n], g["default_alphas"])
+    assert np.allclose(res.obj_fun_trace[0, :n], g["default_Js"], rtol=1e-9, atol=0)
+    assert abs(res.obj_fun_value[0] - float(g["default_J"])) <= 1e-9 * float(g["default_J"])
+    assert rel(res.trajectory[0], g["default_X"]) <= 1e-9
+
+
+@pytest.mark.parametrize("tag", ["TwoLink_T100", "ThreeLink_T100", "ThreeLink_T30"])
+def test_seeded_batch(golden, tag):
+    g = golden(tag)
+    algo = make_algo(str(g["model"]), int(g["T"]))
+    res = algo.solve_batch(g["batch_x0"], g["batch_target"], trace=True).to_host()
+    stable = stable_mask(g)
+    assert stable.sum() >= 0.7 * len(stable)
+    matched = 0
+    for b in range(len(stable)):
+        n = int(g["batch_iters"][b])
+        same = (int(res.iterations[b]) == n and np.array_equal(res.alpha_trace[b, :n], g["batch_alphas"][b, :n]))
+        if stable[b]:
+            assert same, "problem %d: iteration trace differs on a noise-stable problem" % b
+            assert abs(res.obj_fun_value[b] - g["batch_J"][b]) <= 1e-9 * abs(g["batch_J"][b])
+            assert rel(res.trajectory[b], g["batch_X"][b]) <= 1e-9
+        else:   # knife-edge problem: must land inside the reference's own noise envelope
+            its = set(g["noise_iters"][b].tolist()) | {n}
+            lo = min(g["noise_J"][b].min(), g["batch_J"][b])
+            hi = max(g["noise_J"][b].max(), g["batch_J"][b])
+            assert int(res.iterations[b]) in its or lo * (1 - 1e-6) <= res.obj_fun_value[b] <= hi * (1 + 1e-6)
+        matched += same
+    assert matched >= stable.sum()
+
+
+@pytest.mark.parametrize("tag", ["RoboticArm_T100", "RoboticArm_T200"])
+def test_robotic_arm_noise_envelope(golden, tag):
+    """RoboticArm is reference-unstable: require the default problem's iteration
+    trace to match, its cost within the reference's own 1e-15-noise spread (x4 head-room), and every
+    batch problem to end at a cost no worse than 1% above the reference's."""
+    g = golden(tag)
+    algo = make_algo(str(g["model"]), int(g["T"]))
+    res = algo.solve_batch(g["default_x0"][None], g["default_target"][None], trace=True).to_host()
+    Jref = float(g["default_J"])
+    spread = max(np.abs(g["default_noise_J"] - Jref).max() / Jref, 1e-9)
+    iters_seen = set(g["default_noise_iters"].tolist()) | {int(g["default_iters"])}
+    assert int(res.iterations[0]) in iters_seen or abs(res.obj_fun_value[0] - Jref) <= 4 * spread * Jref
+    if int(g["T"]) == 100:
+        assert int(res.iterations[0]) == int(g["default_iters"])
+        assert abs(res.obj_fun_value[0] - Jref) <= max(4 * spread, 2e-6) * Jref
+    bres = algo.solve_batch(g["batch_x0"], g["batch_target"]).to_host()
+    assert np.all(np.isfinite(bres.obj_fun_value))
+    worst = np.maximum(g["batch_J"], g["noise_J"].max(axis=1))
+    assert np.mean(bres.obj_fun_value <= 1.01 * worst) >= 0.75
+
+
+def test_float32_final_cost(golden):
+    g = golden("ThreeLink_T100")
+    algo = make_algo(str(g["model"]), int(g["T"]), dtype="float32")
+    res = algo.solve_batch(g["batch_x0"], g["batch_target"]).to_host()
+    stable = stable_mask(g)
+    err = np.abs(res.obj_fun_value - g["batch_J"]) / np.abs(g["batch_J"])
+    assert np.all(err[stable] <= 1e-4), err
+    assert np.all(res.converged == 1)
+
+
+def test_reference_call_sequence(golden):
+    """Example/ThreeLinkPlanarManipulatorInteractive.py:8-30: solve, retarget, reset, re-solve; and quirk Q7."""
+    from curiousrl_b200 import logger
+    g = golden("ThreeLink_T100")
+    from curiousrl_b200.scenario.dynamic_model import ThreeLinkPlanarManipulator
+    from curiousrl_b200.algorithm.ilqr_solver import BasiciLQR
+    logger.set_level(45)
+    scenario = ThreeLinkPlanarManipulator()
+    algo = BasiciLQR(max_line_search=10)
+    assert algo.init(scenario) is algo
+    assert algo.solve() is None
+    assert abs(algo.get_obj_fun_value() - float(g["default_J"])) <= 1e-9 * float(g["default_J"])
+    assert algo._trajectory.shape == (100, 11, 1)
+    traj = np.asarray(logger.read_from_json()["trajectory"])
+    assert traj.shape == (100, 11, 1) and rel(traj[:, :, 0], g["default_X"]) <= 1e-9
+    # Q7: solving again without resetting the stored cost stops after one rejected iteration
+    J_before = algo.get_obj_fun_value()
+    algo.solve()
+    assert algo.get_obj_fun_value() == J_before and int(algo.last_result.iterations.item()) == 1
+    assert rel(algo._trajectory[:, :, 0], g["default_X_init"]) <= 1e-13
+    # retarget exactly like onclick()
+    b = 3
+    ap = algo.get_obj_add_param()
+    assert ap is scenario.add_param        # aliasing quirk Q8
+    ap[:, 0], ap[:, 1] = g["batch_target"][b]
+    algo.set_obj_add_param(ap)
+    algo.set_obj_fun_value(np.inf)
+    algo.set_init_state(g["batch_x0"][b].reshape(-1, 1))
+    algo.solve()
+    assert int(algo.last_result.iterations.item()) == int(g["batch_iters"][b])
+    assert abs(algo.get_obj_fun_value() - g["batch_J"][b]) <= 1e-9 * g["batch_J"][b]
+
+
+def test_forward_backward_methods(golden):
+    """The reference's per-iteration entry points on NumPy arrays of the reference's shapes."""
+    g = golden("TwoLink_T100")
+    algo = make_algo("TwoLinkPlanarManipulator", 100)
+    X = algo.dynamic_model.eval_traj()
+    assert X.shape == (100, 8, 1) and rel(X[:, :, 0], g["default_X_init"]) <= 1e-14
+    C = algo.obj_fun.eval_hessian_obj_fun(X)
+    c = algo.obj_fun.eval_grad_obj_fun(X)
+    F = algo.dynamic_model.eval_grad_dynamic_model(X)
+    assert C.shape == (100, 8, 8) and c.shape == (100, 8, 1) and F.shape == (100, 6, 8)
+    algo.set_obj_fun_value(np.inf)
+    Js = []
+    for i in range(int(g["default_iters"])):
+        K, k = algo.backward_pass(C, c, F)
+        assert K.shape == (100, 2, 6) and k.shape == (100, 2, 1)
+        X, C, c, F, J, stop = algo.forward_pass(X, K, k)
+        Js.append(J)
+    assert stop and np.allclose(Js, g["default_Js"], rtol=1e-9, atol=0)
+    assert rel(X[:, :, 0], g["default_X"]) <= 1e-9
+
+
+def test_fixed_work_mode_and_options(golden):
+    g = golden("ThreeLink_T30")
+    algo = make_algo("ThreeLinkPlanarManipulator", 30, is_check_stop=False, max_iter=12)
+    res = algo.solve_batch(g["batch_x0"], g["batch_target"], trace=True).to_host()
+    assert np.all(res.iterations == 12) and np.all(res.converged == 0)
+    for b in range(len(g["batch_iters"])):       # cost never increases; after convergence every step is rejected
+        Js = res.obj_fun_trace[b]
+        assert np.all(np.diff(Js) <= 0)
+    none = make_algo("ThreeLinkPlanarManipulator", 30, line_search_method="none", max_iter=3, is_check_stop=False)
+    r2 = none.solve_batch(g["batch_x0"], g["batch_target"], trace=True).to_host()
+    assert np.all(r2.alpha_trace[:, :3] == 0)
+
+
+def test_full_size_properties():
+    """BASELINE config 2 (ThreeLink, B = 65,536, T = 100, FP64): size-independent properties."""
+    from curiousrl_b200.utils.synthetic import synthetic_batch
+    B = 65536
+    x0, tgt = synthetic_batch("ThreeLinkPlanarManipulator", B, seed=1234)
+    algo = make_algo("ThreeLinkPlanarManipulator", 100)
+    res = algo.solve_batch(x0, tgt)
+    J0 = algo._dev.rollout(x0, tgt)[1]
+    assert torch.all(res.converged == 1) and torch.all(res.iterations >= 1)
+    assert torch.all(torch.isfinite(res.obj_fun_value)) and torch.all(res.obj_fun_value <= J0)
+    # returned trajectories are dynamically consistent: re-rolling their actions reproduces them,
+    # and their cost is the reported cost
+    X = res.trajectory
+    Xr, Jr = algo._dev.rollout(x0, tgt, X[:, :, 8:].contiguous())
+    assert torch.allclose(Xr, X, rtol=0, atol=1e-9)
+    assert torch.allclose(algo._dev.cost(X, tgt), res.obj_fun_value, rtol=1e-12, atol=0)
+    assert torch.all(X[:, -1, 8:] == 0) and float(X[:, :, 8:].abs().max()) <= 100.0
+    # shard invariance: any split of the batch gives bit-identical per-trajectory results
+    lo, hi = 1000, 1000 + 4096
+    part = algo.solve_batch(x0[lo:hi], tgt[lo:hi])
+    assert torch.equal(part.obj_fun_value, res.obj_fun_value[lo:hi])
+    assert torch.equal(part.iterations, res.iterations[lo:hi])
+    assert torch.equal(part.trajectory, res.trajectory[lo:hi])
+    # matches the seeded reference statistics (median 14 iterations)
+    med = float(res.iterations.double().median())
+    assert 10 <= med <= 20

@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""Benchmark of the batched-iLQR hot path (BASELINE.json metric: iLQR trajectory-iterations/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # B200 arm (this repo)
+    python bench.py --impl reference [...]                         # reference arm: CPU solver on host cores
+
+Workload (config.workload): BASELINE.json configs[1] - ThreeLinkPlanarManipulator, 65,536 random
+initial states/targets per GPU (generator of SURVEY.md section 8(d), seed 1234 + rank), T = 100, FP64,
+`BasiciLQR(max_line_search=10)` defaults, solved to convergence.  One *step* = one whole-batch solve
+(one persistent-kernel launch).  A trajectory-iteration = one backward pass + one line-search
+forward pass of one trajectory; the number executed is data dependent and is summed from the
+solver's own per-trajectory iteration counts.
+
+value   device-timed throughput, inputs resident in HBM (CUDA events on the launch stream).
+e2e     same metric through the public API (`BasiciLQR.solve_batch`) from pinned HOST buffers:
+        H2D of initial states/targets and D2H of costs/iteration counts/flags/trajectories inside
+        the timed region.
+roofline  achieved algorithmic HBM bytes/s of the solve kernel vs the measured copy bandwidth.
+cpu_baseline  the CPU oracle port (numba substrate, as the reference) on the host cores, N=1 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MODEL = "ThreeLinkPlanarManipulator"
+METRIC = "ilqr_trajectory_iterations_per_sec"
+UNIT = "traj-iter/s"
+MAX_LINE_SEARCH = 10
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=65536, help="trajectories per GPU")
+    ap.add_argument("--horizon", type=int, default=100)
+    ap.add_argument("--dtype", default="float64", choices=["float64", "float32"])
+    ap.add_argument("--model", default=MODEL)
+    ap.add_argument("--mode", default="converge", choices=["converge", "fixed"],
+                    help="converge: reference defaults; fixed: is_check_stop=False, max_iter=20")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="trajectories per core for the CPU baseline (0 = auto)")
+    ap.add_argument("--grid-blocks", type=int, default=0)
+    return ap.parse_args()
+
+
+def bytes_per_traj_iter(n, m, T, s):
+    """compulsory HBM traffic of one trajectory-iteration, s*T*(3d + 2m(n+1))."""
+    d = n + m
+    return s * T * (3 * d + 2 * m * (n + 1))
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.samples, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r.split(", ") for ts, r in self.samples if t0 <= ts <= t1 + 0.2] or [r.split(", ") for _, r in self.samples]
+        if not rows:
+            return None
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in rows for i in range(4) if len(r) >= 6 and r[2 + i].strip() == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(rows[0][1]) if rows else None,
+                "reasons": reasons, "samples": len(rows)}
+
+
+# ----------------------------------------------------------------------------- CPU baseline (oracle port)
+_WORKER = {}
+
+
+def _cpu_init(model, T, barrier):
+    """Per-process set-up: build the oracle problem and pay the numba JIT once (untimed, as the
+    reference itself excludes its compile iteration, basic_ilqr.py:82-83)."""
+    for var in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "NUMBA_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = "1"
+    import warnings
+    warnings.filterwarnings("ignore")
+    import curiousrl_b200.scenario.dynamic_model as models
+    from curiousrl_b200.utils.synthetic import synthetic_batch
+    from oracle import ilqr_numpy as orc                 # CPU baseline / reference arm: the one place bench.py runs the oracle
+    prob = orc.Problem(getattr(models, model)(T=T), use_numba=True)
+    x0, tgt = synthetic_batch(model, 1, seed=99)
+    orc.solve(prob, x0[0], tgt[0], max_line_search=MAX_LINE_SEARCH, max_iter=3)
+    _WORKER["prob"], _WORKER["orc"], _WORKER["barrier"] = prob, orc, barrier
+
+
+def _cpu_solve(job):
+    x0, tgt = job
+    orc, prob = _WORKER["orc"], _WORKER["prob"]
+    t0 = time.perf_counter()
+    iters = 0
+    for b in range(x0.shape[0]):
+        iters += orc.solve(prob, x0[b], tgt[b], max_line_search=MAX_LINE_SEARCH)["iters"]
+    return iters, time.perf_counter() - t0
+
+
+class CpuReference:
+    """Pool of one worker per host core, each running the CPU oracle port single-threaded."""
+
+    def __init__(self, model, T, cores=None):
+        import multiprocessing as mp
+        self.model = model
+        self.cores = cores or min(os.cpu_count() or 1, 64)
+        ctx = mp.get_context("spawn")
+        self.pool = ctx.Pool(self.cores, initializer=_cpu_init, initargs=(model, T, ctx.Barrier(self.cores)))
+        self.pool.map(_ready, range(self.cores), chunksize=1)   # returns once every worker finished its JIT warm-up
+
+    def run(self, per_core, seed):
+        """Solve the first per_core*cores trajectories of the seeded batch; returns (iters, seconds)."""
+        from curiousrl_b200.utils.synthetic import synthetic_batch
+        x0, tgt = synthetic_batch(self.model, per_core * self.cores, seed=seed)
+        jobs = [(x0[c::self.cores], tgt[c::self.cores]) for c in range(self.cores)]
+        t0 = time.perf_counter()
+        out = self.pool.map(_cpu_solve, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+        return sum(o[0] for o in out), wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def _ready(_):
+    _WORKER["barrier"].wait(timeout=600)      # one task per worker: nobody passes until all are initialised
+    return 0
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_core = args.cpu_sample or 16
+    ref = CpuReference(args.model, args.horizon)
+    iters_tot, wall_tot = 0, 0.0
+    for step in range(args.warmup + args.steps):
+        iters, wall = ref.run(per_core, seed=1234)
+        if step >= args.warmup:
+            iters_tot += iters
+            wall_tot += wall
+    ref.close()
+    value = iters_tot / wall_tot
+    sample = ("each step = the first %d trajectories of the seeded batch (%d per core), CPU oracle port on the numba+BLAS "
+              "substrate of the reference, one single-threaded worker per core, JIT warm-up excluded" % (
+                  per_core * ref.cores, per_core))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * wall_tot / max(1, args.steps), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_gpus):
+    return {"workload": "%s iLQR, batch %d random initial states per GPU, T=%d, %s, BasiciLQR(max_line_search=%d), %s" % (
+                args.model, args.batch, args.horizon, "FP64" if args.dtype == "float64" else "FP32", MAX_LINE_SEARCH,
+                "to convergence (relative 1e-6, max_iter 1000)" if args.mode == "converge" else "fixed work (20 iterations)"),
+            "model": args.model, "batch_per_gpu": args.batch, "global_batch": args.batch * n_gpus, "horizon": args.horizon,
+            "mode": args.mode, "parallelism": "dp%d (independent shards, terminal gather of J/iters/flags)" % n_gpus,
+            "cache": "working set (solver workspace ~1.3 GB + 0.6 GB results) exceeds the 126 MB L2; "
+                     "a 512 MB buffer is overwritten between timed steps"}
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from curiousrl_b200 import logger
+    from curiousrl_b200.algorithm.ilqr_solver import BasiciLQR
+    from curiousrl_b200.distributed import gather_results
+    import curiousrl_b200.scenario.dynamic_model as models
+    from curiousrl_b200.utils.synthetic import synthetic_batch
+
+    logger.set_level(45)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, T = args.batch, args.horizon
+    kw = dict(max_line_search=MAX_LINE_SEARCH, dtype=args.dtype, grid_blocks=args.grid_blocks)
+    if args.mode == "fixed":
+        kw.update(is_check_stop=False, max_iter=20)
+    algo = BasiciLQR(**kw).init(getattr(models, args.model)(T=T))
+    dm = algo._dev
+    x0_h, tgt_h = synthetic_batch(args.model, B, seed=1234 + rank)
+    np_dt = np.float64 if args.dtype == "float64" else np.float32
+    x0_pin = torch.from_numpy(x0_h.astype(np_dt)).pin_memory()
+    tgt_pin = torch.from_numpy(tgt_h.astype(np_dt)).pin_memory()
+    x0_d, tgt_d = x0_pin.to(dev), tgt_pin.to(dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    out = None
+    total_B = B * world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        nonlocal out
+        out = algo.solve_batch(x0_d, tgt_d, out=out)
+        if world > 1:
+            return gather_results(out.obj_fun_value, out.iterations, out.converged, total_B)
+        return out
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        step_device()
+    barrier()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_wall0 = time.time()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()
+        starts[i].record()
+        res = step_device()
+        ends[i].record()
+    barrier()
+    t_wall1 = time.time()
+    ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    iters_local = int(out.iterations.sum().item())                      # identical every step (deterministic)
+    conv_local = int(out.converged.sum().item())
+    stats = torch.tensor([ms, float(iters_local), float(conv_local)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, iters_all, conv_all = float(mx[0]), float(sm[1]), float(sm[2])
+    else:
+        iters_all, conv_all = float(iters_local), float(conv_local)
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    ms_per_step = ms / args.steps
+    value = iters_all / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API from pinned host memory
+    J_h = torch.empty(B, dtype=torch.float64).pin_memory()
+    it_h = torch.empty(B, dtype=torch.int32).pin_memory()
+    cv_h = torch.empty(B, dtype=torch.uint8).pin_memory()
+    X_h = torch.empty((B, T, dm.d), dtype=dm.dtype).pin_memory()
+
+    def step_e2e():
+        r = algo.solve_batch(x0_pin.to(dev, non_blocking=True), tgt_pin.to(dev, non_blocking=True), out=out)
+        if world > 1:
+            gather_results(r.obj_fun_value, r.iterations, r.converged, total_B)
+        J_h.copy_(r.obj_fun_value, non_blocking=True)
+        it_h.copy_(r.iterations, non_blocking=True)
+        cv_h.copy_(r.converged, non_blocking=True)
+        X_h.copy_(r.trajectory, non_blocking=True)
+        torch.cuda.synchronize()
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = iters_all / float(e2e_t[0])
+    h2d = x0_pin.numel() * x0_pin.element_size() + tgt_pin.numel() * tgt_pin.element_size()
+    d2h = sum(t.numel() * t.element_size() for t in (J_h, it_h, cv_h, X_h))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    s = 8 if args.dtype == "float64" else 4
+    bpi = bytes_per_traj_iter(dm.n, dm.m, T, s)
+    peak, peak_src = measured_hbm_peak()
+    achieved = (iters_local * bpi) / (ms_per_step * 1e-3) / 1e9           # rank 0's kernel: its own bytes / its own time
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if args.dtype == "float64" else "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "traj_iters_per_step": iters_all, "converged_fraction": conv_all / total_B,
+            "mean_iters_per_traj": iters_all / total_B,
+            "gpu_launches": args.steps,       # one persistent solve_kernel per step (+ a 256 B memset node)
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_s * 1e3},
+            "roofline": {"bound": "hbm", "kernel": "solve_kernel<%s,%s>" % (args.model, args.dtype), "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_traj_iter": bpi}}
+    if world == 1 and not args.no_cpu_baseline:
+        per_core = args.cpu_sample or 32
+        try:
+            ref = CpuReference(args.model, T)
+            iters, wall = ref.run(per_core, seed=1234)
+            ref.close()
+            line["cpu_baseline"] = {"value": iters / wall, "unit": UNIT, "cores": ref.cores, "kind": "port",
+                                    "sample": "first %d trajectories of the same seeded batch (%d per core; %d traj-iters in "
+                                              "%.1f s), CPU oracle port on the reference's numba+BLAS substrate, JIT warm-up "
+                                              "excluded" % (per_core * ref.cores, per_core, iters, wall)}
+        except Exception as exc:      # the baseline is reporting only; never lose the GPU line
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "failed: %r" % (exc,)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -15,7 +15,8 @@ For every config it records, with `BasiciLQR(max_line_search=10)`:
   target, iterations, final cost, final trajectory, step-index and cost traces;
 * the same batch re-solved with K, k perturbed by 1e-15 relative noise
    so tests can tell noise-stable problems from
-  knife-edge ones.
+  knife-edge ones, and by 6e-8 relative noise (float32 round-off) to
+  delimit what an FP32 solver can reproduce.
 """
 import os
 import sys
@@ -49,6 +50,7 @@ CONFIGS = {
 MAX_LINE_SEARCH = 10
 NOISE_RUNS = 4
 NOISE_EPS = 1e-15
+NOISE_EPS_F32 = 6e-8      # float32 unit round-off: the perturbation scale an FP32 solver injects
 
 
 class Recorder:
@@ -66,6 +68,7 @@ class Recorder:
         algo.forward_pass = self.forward_pass
         algo.backward_pass = self.backward_pass
         self.noise_rng = None
+        self.noise_eps = NOISE_EPS
 
     def reset(self):
         self.Js, self.alphas, self.rollouts, self.stages = [], [], [], {}
@@ -84,8 +87,8 @@ class Recorder:
     def backward_pass(self, C, c, F):
         K, k = self._backward(C, c, F)
         if self.noise_rng is not None:
-            K = K * (1.0 + NOISE_EPS * self.noise_rng.standard_normal(K.shape))
-            k = k * (1.0 + NOISE_EPS * self.noise_rng.standard_normal(k.shape))
+            K = K * (1.0 + self.noise_eps * self.noise_rng.standard_normal(K.shape))
+            k = k * (1.0 + self.noise_eps * self.noise_rng.standard_normal(k.shape))
         if self.it in self.stage_iters:
             self._bw = dict(C=C.copy(), c=c[:, :, 0].copy(), F=F.copy(), K=K.copy(), k=k[:, :, 0].copy())
         return K, k
@@ -115,9 +118,10 @@ class Recorder:
         return out
 
 
-def run(algo, rec, x0=None, target=None, noise_seed=None):
+def run(algo, rec, x0=None, target=None, noise_seed=None, noise_eps=NOISE_EPS):
     rec.reset()
     rec.noise_rng = None if noise_seed is None else np.random.default_rng(noise_seed)
+    rec.noise_eps = noise_eps
     if target is not None:
         ap = algo.get_obj_add_param()
         ap[:, 0] = target[0]
@@ -192,6 +196,14 @@ def make(tag):
             ref = finals[b]["X"]
             n_Xerr[b, s] = np.max(np.abs(r["X"] - ref)) / max(1.0, np.max(np.abs(ref)))
     out["noise_iters"], out["noise_J"], out["noise_Xerr"] = n_iters, n_J, n_Xerr
+    # the same with float32-sized noise: which problems can an FP32 solver be expected to reproduce?
+    f_iters = np.zeros((batch, NOISE_RUNS), dtype=np.int32)
+    f_J = np.zeros((batch, NOISE_RUNS))
+    for b in range(batch):
+        for s in range(NOISE_RUNS):
+            r = run(algo, rec, x0s[b], targets[b], noise_seed=5000 + 1000 * b + s, noise_eps=NOISE_EPS_F32)
+            f_iters[b, s], f_J[b, s] = r["iters"], r["J"]
+    out["noise32_iters"], out["noise32_J"] = f_iters, f_J
     d_iters = np.zeros(NOISE_RUNS, dtype=np.int32)
     d_J = np.zeros(NOISE_RUNS)
     for s in range(NOISE_RUNS):

@@ -1,0 +1,159 @@
+"""The kernels' numerical core, compiled for the host (tests/hostsim), against the reference's
+golden vectors and the CPU oracle.  Same tolerances and protocol as the `-m gpu` parity tests;
+this is what lets the device math be checked in a container without a GPU.  (The shipped
+library has no host path - see tests/hostsim/hostsim.cpp.)
+"""
+import numpy as np
+import pytest
+
+from conftest import make_problem
+from hostsim import HostSim
+from oracle import ilqr_numpy as orc
+
+TAGS = ["TwoLink_T100", "ThreeLink_T100", "RoboticArm_T100", "RoboticArm_T200", "ThreeLink_T30"]
+CHAINS = ["TwoLink_T100", "ThreeLink_T100", "ThreeLink_T30"]
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(1e-300, np.abs(b).max()))
+
+
+def stable_mask(g, tol=1e-9):
+    it_ok = np.all(g["noise_iters"] == g["batch_iters"][:, None], axis=1)
+    J_ok = np.all(np.abs(g["noise_J"] - g["batch_J"][:, None]) <= tol * np.abs(g["batch_J"][:, None]), axis=1)
+    return it_ok & J_ok & np.all(g["noise_Xerr"] <= tol, axis=1)
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_stage_parity(golden, tag):
+    g = golden(tag)
+    T, model = int(g["T"]), str(g["model"])
+    hs = HostSim(model)
+    tgt = g["default_target"]
+    X, J = hs.rollout(g["default_x0"], tgt, T)
+    assert rel(X, g["default_X_init"]) <= 1e-15
+    arm = model == "RoboticArmTracking"
+    for it in g["stage_iters"]:
+        pre = "stage%d_" % it
+        Xs = g[pre + "X"]
+        F, c, C = hs.derivs(Xs, tgt)
+        assert rel(F, g[pre + "F"]) <= 1e-13 and rel(c, g[pre + "c"]) <= 1e-15 and np.array_equal(C, g[pre + "C"])
+        K, k = hs.backward(Xs, tgt)
+        Kd, kd = hs.backward_dense(g[pre + "F"], g[pre + "c"], g[pre + "C"])
+        if not arm:
+            assert rel(K, g[pre + "K"]) <= 1e-10 and rel(k, g[pre + "k"]) <= 1e-10
+            assert rel(Kd, g[pre + "K"]) <= 1e-10 and rel(kd, g[pre + "k"]) <= 1e-10
+        elif T == 100 and it == 0:
+            assert rel(K, g[pre + "K"]) <= 1e-6 and rel(Kd, g[pre + "K"]) <= 1e-9
+        assert np.all(K[-1] == 0) and np.all(np.signbit(K[-1]))          # -solve(Quu, 0) = -0.0
+        for alpha, Xc, Jc in zip(g[pre + "cand_alpha"], g[pre + "cand_X"], g[pre + "cand_J"]):
+            Xn, Jn = hs.update(Xs, g[pre + "K"], g[pre + "k"], float(alpha), tgt)
+            assert rel(Xn, Xc) <= 1e-13 and abs(Jn - Jc) <= 1e-14 * abs(Jc)
+            assert np.all(Xn[-1, hs.n:] == 0)
+
+
+@pytest.mark.parametrize("tag", CHAINS)
+def test_structured_equals_dense_riccati(golden, tag):
+    """Pruning structural zeros / ones of F must not change the recursion beyond rounding."""
+    g = golden(tag)
+    hs = HostSim(str(g["model"]))
+    X = g["stage1_X"]
+    F, c, C = hs.derivs(X, g["default_target"])
+    K, k = hs.backward(X, g["default_target"])
+    Kd, kd = hs.backward_dense(F, c, C)
+    assert rel(K, Kd) <= 1e-11 and rel(k, kd) <= 1e-11
+
+
+@pytest.mark.parametrize("tag", CHAINS)
+def test_solve_default_and_batch(golden, tag):
+    g = golden(tag)
+    T = int(g["T"])
+    hs = HostSim(str(g["model"]))
+    r = hs.solve(g["default_x0"], g["default_target"], T)
+    n = int(g["default_iters"])
+    assert r["iters"] == n and r["converged"]
+    assert np.array_equal(r["alphas"], g["default_alphas"])
+    assert np.allclose(r["Js"], g["default_Js"], rtol=1e-9, atol=0)
+    assert rel(r["X"], g["default_X"]) <= 1e-9
+    stable = stable_mask(g)
+    assert stable.sum() >= 0.7 * len(stable)
+    for b in range(len(stable)):
+        r = hs.solve(g["batch_x0"][b], g["batch_target"][b], T)
+        nb = int(g["batch_iters"][b])
+        if stable[b]:
+            assert r["iters"] == nb and np.array_equal(r["alphas"], g["batch_alphas"][b, :nb])
+            assert abs(r["J"] - g["batch_J"][b]) <= 1e-9 * g["batch_J"][b]
+            assert rel(r["X"], g["batch_X"][b]) <= 1e-9
+        else:   # knife-edge problem: terminate normally, no worse than the reference's worst outcome
+            hi = max(g["noise_J"][b].max(), g["batch_J"][b])
+            assert r["converged"] and r["J"] <= hi * (1 + 1e-3)
+
+
+def test_robotic_arm_default_matches_within_envelope(golden):
+    g = golden("RoboticArm_T100")
+    hs = HostSim("RoboticArmTracking")
+    r = hs.solve(g["default_x0"], g["default_target"], 100)
+    Jref = float(g["default_J"])
+    spread = max(np.abs(g["default_noise_J"] - Jref).max() / Jref, 1e-9)
+    assert r["iters"] == int(g["default_iters"]) and np.array_equal(r["alphas"], g["default_alphas"])
+    assert abs(r["J"] - Jref) <= max(4 * spread, 2e-6) * Jref
+
+
+@pytest.mark.parametrize("tag", ["TwoLink_T100", "ThreeLink_T100"])
+def test_float32_final_cost(golden, tag):
+    """FP32 arithmetic with FP64 cost accumulation: final cost <= 1e-4 relative wherever the reference
+    itself is reproducible to 1e-4 under float32-sized (6e-8) perturbations of K, k."""
+    g = golden(tag)
+    hs = HostSim(str(g["model"]), "f32")
+    stable = np.all(np.abs(g["noise32_J"] - g["batch_J"][:, None]) <= 1e-4 * np.abs(g["batch_J"][:, None]), axis=1)
+    # pure-FP32 costs carry ~1e-6 relative noise, which ends slowly converging solves early (DESIGN.md,
+    # "FP32 mode"); the 1e-4 bar is asserted on problems the reference finishes within 30 iterations
+    stable &= g["batch_iters"] <= 30
+    assert stable.sum() >= 0.4 * len(stable)
+    for b in range(len(stable)):
+        r = hs.solve(g["batch_x0"][b], g["batch_target"][b], 100)
+        assert r["converged"]
+        if stable[b]:
+            assert abs(r["J"] - g["batch_J"][b]) <= 1e-4 * g["batch_J"][b], (b, r["J"], g["batch_J"][b])
+
+
+def test_quirks_and_options(golden):
+    g = golden("ThreeLink_T30")
+    hs = HostSim("ThreeLinkPlanarManipulator")
+    x0, tgt = g["batch_x0"][0], g["batch_target"][0]
+    # fixed-work mode: exactly max_iter iterations, cost never increases, rejected steps keep X
+    r = hs.solve(x0, tgt, 30, max_iter=14, is_check_stop=False)
+    assert r["iters"] == 14 and not r["converged"] and np.all(np.diff(r["Js"]) <= 0)
+    # first iteration is accepted unconditionally at alpha = 1 (J_last starts at inf)
+    assert r["alphas"][0] == 0
+    # Q7: a finite stored cost below the start makes every step fail -> stop after 1 iteration with
+    # the *initial* rollout and the stored cost returned
+    X_init, _ = hs.rollout(x0, tgt, 30)
+    r2 = hs.solve(x0, tgt, 30, J_init=1.0)
+    assert r2["iters"] == 1 and r2["J"] == 1.0 and r2["alphas"][0] == -1 and np.array_equal(r2["X"], X_init)
+    # "none" line search always takes alpha = 1; "vanilla" stopping uses |dJ|
+    r3 = hs.solve(x0, tgt, 30, line_search_method=2, max_iter=3, is_check_stop=False)
+    assert np.all(r3["alphas"] == 0)
+    r4 = hs.solve(x0, tgt, 30, stopping_method=1, stopping_criterion=1e-3)
+    ref = orc.solve(make_problem("ThreeLinkPlanarManipulator", 30), x0, tgt, stopping_method="vanilla",
+                    stopping_criterion=1e-3)
+    assert r4["iters"] == ref["iters"] and abs(r4["J"] - ref["J"]) <= 1e-9 * ref["J"]
+
+
+def test_time_varying_target_and_given_actions(golden):
+    """add_param [T, p] that changes over the horizon, and a non-zero initial action sequence."""
+    T = 30
+    prob = make_problem("ThreeLinkPlanarManipulator", T)
+    hs = HostSim("ThreeLinkPlanarManipulator")
+    rng = np.random.default_rng(7)
+    P = np.stack([2 + 0.5 * np.sin(np.arange(T) / 5.0), 2 + 0.5 * np.cos(np.arange(T) / 5.0)], axis=1)
+    U0 = rng.uniform(-150, 150, (T, 3))           # partly outside the +-100 box: exercises the clamp order
+    x0 = golden("ThreeLink_T30")["batch_x0"][1]
+    X, J = hs.rollout(x0, P, T, u0=U0)
+    Xr = orc.rollout(prob, x0, U0)
+    assert rel(X, Xr) <= 1e-14 and abs(J - orc.cost(prob, Xr, P)) <= 1e-14 * J
+    assert np.all(np.abs(X[:-1, 8:]) <= 100) and np.array_equal(X[-1, 8:], U0[-1])   # last row never clamped
+    r = hs.solve(x0, P, T, u0=U0)
+    ref = orc.solve(prob, x0, P, U0)
+    assert r["iters"] == ref["iters"] and abs(r["J"] - ref["J"]) <= 1e-9 * ref["J"] and rel(r["X"], ref["X"]) <= 1e-9

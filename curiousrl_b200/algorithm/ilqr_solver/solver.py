@@ -135,7 +135,8 @@ class iLQRWrapper(AlgoWrapper):
         return _native.SolverOpts(int(max_iter), int(bool(is_check_stop)), float(self._stopping_criterion),
                                   int(self._max_line_search), float(self._gamma),
                                   _native.LINE_SEARCH_IDS[self._line_search_method],
-                                  _native.STOPPING_IDS[self._stopping_method], int(getattr(self, "_grid_blocks", 0)), 0)
+                                  _native.STOPPING_IDS[self._stopping_method], int(getattr(self, "_grid_blocks", 0)),
+                                  int(getattr(self, "_occupancy", 0)))
 
     def _params_for(self, B: int) -> torch.Tensor:
         """The solver's current add_param ([T, p], reference semantics) as a device tensor shared by B problems."""
@@ -192,7 +193,7 @@ class BasiciLQR(iLQRWrapper):
 
     def __init__(self, max_iter=1000, is_check_stop=True, stopping_criterion=1e-6, max_line_search=50, gamma=0.5,
                  line_search_method="vanilla", stopping_method="relative", dtype="float64", device=None, verify=True,
-                 grid_blocks=0):
+                 grid_blocks=0, occupancy=0):
         super().__init__(stopping_criterion=stopping_criterion, max_line_search=max_line_search, gamma=gamma,
                          line_search_method=line_search_method, stopping_method=stopping_method,
                          max_iter=max_iter, is_check_stop=is_check_stop)
@@ -202,6 +203,7 @@ class BasiciLQR(iLQRWrapper):
         self._device = device
         self._verify = verify
         self._grid_blocks = grid_blocks
+        self._occupancy = occupancy      # resident CTAs/SM variant of the solve kernel (0 = default)
         self._trajectory = None
         self.last_result: Optional[BatchResult] = None
 

@@ -57,7 +57,7 @@ CRL_HD double rollout_open(const R* x0, int sx0, const R* U, int su_t, const Par
     double J = 0.0;
     for (int t = 0; t < T; ++t) {
         const bool last = (t == T - 1);
-        if (!last) Mdl::template step<R>(xu, xn);            // from the unclamped row
+        if (!last) model_step<Mdl, R>(xu, xn);            // from the unclamped row
         if (!last && ub.active) {
             CRL_UNROLL for (int a = 0; a < M; ++a) xu[N + a] = clamp_(xu[N + a], ub.lo, ub.hi);
         }
@@ -86,25 +86,48 @@ CRL_HD double rollout_closed(View<R, Mdl::D, SCX> Xold, View<R, Mdl::M * KN, SCK
         const R* row = Xold.row(0);
         CRL_UNROLL for (int i = 0; i < D; ++i) xu[i] = Xold.ld(row, i);   // row 0 copied whole (:121)
     }
+    // software pipeline: the inputs of step t+1 (old states/actions, K, k) are fetched into
+    // registers while step t computes, so one warp keeps its loads in flight across its own math
+    R xo_n[KN], uo_n[M], K_n[M * KN], k_n[M];
+    if (T > 1) {
+        const R* xo = Xold.row(0);
+        const R* Kr = Kv.row(0);
+        const R* kr = kv.row(0);
+        CRL_UNROLL for (int j = 0; j < KN; ++j) xo_n[j] = Xold.ld(xo, j);
+        CRL_UNROLL for (int a = 0; a < M; ++a) uo_n[a] = Xold.ld(xo, N + a);
+        CRL_UNROLL for (int j = 0; j < M * KN; ++j) K_n[j] = Kv.ld(Kr, j);
+        CRL_UNROLL for (int a = 0; a < M; ++a) k_n[a] = kv.ld(kr, a);
+    }
     double J = 0.0;
     for (int t = 0; t < T - 1; ++t) {
-        const R* xo = Xold.row(t);
-        const R* Kr = Kv.row(t);
-        const R* kr = kv.row(t);
+        R xo_c[KN], uo_c[M], K_c[M * KN], k_c[M];
+        CRL_UNROLL for (int j = 0; j < KN; ++j) xo_c[j] = xo_n[j];
+        CRL_UNROLL for (int a = 0; a < M; ++a) uo_c[a] = uo_n[a];
+        CRL_UNROLL for (int j = 0; j < M * KN; ++j) K_c[j] = K_n[j];
+        CRL_UNROLL for (int a = 0; a < M; ++a) k_c[a] = k_n[a];
+        if (t + 1 < T - 1) {
+            const R* xo = Xold.row(t + 1);
+            const R* Kr = Kv.row(t + 1);
+            const R* kr = kv.row(t + 1);
+            CRL_UNROLL for (int j = 0; j < KN; ++j) xo_n[j] = Xold.ld(xo, j);
+            CRL_UNROLL for (int a = 0; a < M; ++a) uo_n[a] = Xold.ld(xo, N + a);
+            CRL_UNROLL for (int j = 0; j < M * KN; ++j) K_n[j] = Kv.ld(Kr, j);
+            CRL_UNROLL for (int a = 0; a < M; ++a) k_n[a] = kv.ld(kr, a);
+        }
         R dx[KN];
-        CRL_UNROLL for (int j = 0; j < KN; ++j) dx[j] = xu[j] - Xold.ld(xo, j);
+        CRL_UNROLL for (int j = 0; j < KN; ++j) dx[j] = xu[j] - xo_c[j];
         CRL_UNROLL for (int a = 0; a < M; ++a) {
-            R acc = Kv.ld(Kr, a * KN) * dx[0];
-            CRL_UNROLL for (int j = 1; j < KN; ++j) acc = fmadd(Kv.ld(Kr, a * KN + j), dx[j], acc);
-            R du = acc + alpha * kv.ld(kr, a);
-            R u = Xold.ld(xo, N + a) + du;
+            R acc = K_c[a * KN] * dx[0];
+            CRL_UNROLL for (int j = 1; j < KN; ++j) acc = fmadd(K_c[a * KN + j], dx[j], acc);
+            R du = acc + alpha * k_c[a];
+            R u = uo_c[a] + du;
             if (ub.active) u = clamp_(u, ub.lo, ub.hi);
             xu[N + a] = u;
         }
         R* row = Xnew.row(t);
         CRL_UNROLL for (int i = 0; i < D; ++i) Xnew.st(row, i, xu[i]);
         J = J + step_cost<Mdl, R>(xu, prm, t);
-        Mdl::template step<R>(xu, xn);
+        model_step<Mdl, R>(xu, xn);
         CRL_UNROLL for (int i = 0; i < N; ++i) xu[i] = xn[i];
     }
     if (T > 1) {
@@ -114,6 +137,90 @@ CRL_HD double rollout_closed(View<R, Mdl::D, SCX> Xold, View<R, Mdl::M * KN, SCK
     CRL_UNROLL for (int i = 0; i < D; ++i) Xnew.st(row, i, xu[i]);
     J = J + step_cost<Mdl, R>(xu, prm, T - 1);
     return J;
+}
+
+// -----------------------------------------------------------------------------------------
+// NA step sizes in ONE pass over the stored data: the old trajectory, K and k are read once
+// and shared by all candidates (this is what makes the line search move its algorithmic bytes
+// only), and the NA independent rollouts give each lane NA-way instruction-level parallelism.
+// Per candidate the arithmetic is exactly rollout_closed's, so every J[a] is bit-identical to
+// a separate single-alpha call.  Only the candidate with index `keep` (per lane, -1 = none)
+// is written to Xnew; a different winner is re-materialised by one rollout_closed call.
+template <class Mdl, class R, int NA, int KN, int SCX, int SCK, int SCXN>
+CRL_HD void rollout_multi(View<R, Mdl::D, SCX> Xold, View<R, Mdl::M * KN, SCK> Kv, View<R, Mdl::M, SCK> kv,
+                          const R (&alpha)[NA], const ParamRef<R>& prm, const Bounds<R>& ub, int T, int keep,
+                          View<R, Mdl::D, SCXN> Xnew, double (&J)[NA]) {
+    constexpr int N = Mdl::N, M = Mdl::M, D = Mdl::D;
+    R xu[NA][D];
+    {
+        const R* row = Xold.row(0);
+        CRL_UNROLL for (int i = 0; i < D; ++i) {
+            const R v = Xold.ld(row, i);
+            CRL_UNROLL for (int a = 0; a < NA; ++a) xu[a][i] = v;
+        }
+    }
+    CRL_UNROLL for (int a = 0; a < NA; ++a) J[a] = 0.0;
+    for (int t = 0; t < T - 1; ++t) {
+        const R* xo = Xold.row(t);
+        const R* Kr = Kv.row(t);
+        const R* kr = kv.row(t);
+        if (t + 1 < T - 1) {                 // next step's inputs start their trip from HBM now
+            Xold.prefetch(t + 1);
+            Kv.prefetch(t + 1);
+            kv.prefetch(t + 1);
+        }
+        R xo_c[KN], uo_c[M], K_c[M * KN], k_c[M];
+        CRL_UNROLL for (int j = 0; j < KN; ++j) xo_c[j] = Xold.ld(xo, j);
+        CRL_UNROLL for (int a = 0; a < M; ++a) uo_c[a] = Xold.ld(xo, N + a);
+        CRL_UNROLL for (int j = 0; j < M * KN; ++j) K_c[j] = Kv.ld(Kr, j);
+        CRL_UNROLL for (int a = 0; a < M; ++a) k_c[a] = kv.ld(kr, a);
+        CRL_UNROLL for (int c = 0; c < NA; ++c) {
+            R dx[KN];
+            CRL_UNROLL for (int j = 0; j < KN; ++j) dx[j] = xu[c][j] - xo_c[j];
+            CRL_UNROLL for (int a = 0; a < M; ++a) {
+                R acc = K_c[a * KN] * dx[0];
+                CRL_UNROLL for (int j = 1; j < KN; ++j) acc = fmadd(K_c[a * KN + j], dx[j], acc);
+                R du = acc + alpha[c] * k_c[a];
+                R u = uo_c[a] + du;
+                if (ub.active) u = clamp_(u, ub.lo, ub.hi);
+                xu[c][N + a] = u;
+            }
+        }
+        if (keep >= 0) {
+            R* row = Xnew.row(t);
+            CRL_UNROLL for (int i = 0; i < D; ++i) {
+                R v = xu[0][i];
+                CRL_UNROLL for (int c = 1; c < NA; ++c) v = (keep == c) ? xu[c][i] : v;
+                Xnew.st(row, i, v);
+            }
+        }
+        {
+            constexpr int NG = Mdl::NANG;
+            R ang[NA * NG], sn[NA * NG], cs[NA * NG];
+            CRL_UNROLL for (int c = 0; c < NA; ++c) Mdl::template angles<R>(xu[c], ang + c * NG);
+            sincos_batch<NA * NG, R>(ang, sn, cs);       // all candidates' trigonometry as one straight-line block
+            CRL_UNROLL for (int c = 0; c < NA; ++c) {
+                R xn[N];
+                J[c] = J[c] + step_cost<Mdl, R>(xu[c], prm, t);
+                Mdl::template step_trig<R>(xu[c], sn + c * NG, cs + c * NG, xn);
+                CRL_UNROLL for (int i = 0; i < N; ++i) xu[c][i] = xn[i];
+            }
+        }
+    }
+    CRL_UNROLL for (int c = 0; c < NA; ++c) {
+        if (T > 1) {
+            CRL_UNROLL for (int a = 0; a < M; ++a) xu[c][N + a] = R(0);
+        }
+        J[c] = J[c] + step_cost<Mdl, R>(xu[c], prm, T - 1);
+    }
+    if (keep >= 0) {
+        R* row = Xnew.row(T - 1);
+        CRL_UNROLL for (int i = 0; i < D; ++i) {
+            R v = xu[0][i];
+            CRL_UNROLL for (int c = 1; c < NA; ++c) v = (keep == c) ? xu[c][i] : v;
+            Xnew.st(row, i, v);
+        }
+    }
 }
 
 // -----------------------------------------------------------------------------------------
@@ -174,12 +281,17 @@ CRL_HD void lu_solve(R (&a)[M][M], R (&b)[M][NR]) {
 // Value-function state carried down the horizon.  Because the output entries y never feed
 // back (F[:, y] = 0) the exact recursion keeps V block diagonal: V = diag(Vss, diag(vyy)),
 // with vyy = C_yy after the first step, and K[:, y] = 0.
+// Vss is kept SYMMETRIC (upper triangle, mirrored on read).  The reference never symmetrises
+// V, but its asymmetry is pure rounding noise (~1e-16 relative) - well inside the 1e-15
+// perturbation under which its own results are reproducible - and
+// symmetric storage halves the live registers of the pass.
 template <class Mdl, class R>
 struct ValueFn {
-    R Vss[Mdl::NS][Mdl::NS];
+    R Vss[Mdl::NS][Mdl::NS];      // only [i][j] with i <= j is meaningful
     R vs[Mdl::NS];
     R vyy[Mdl::NO];
     R vy[Mdl::NO];
+    CRL_HD R V(int i, int j) const { return i <= j ? Vss[i][j] : Vss[j][i]; }
     CRL_HD void clear() {
         CRL_UNROLL for (int i = 0; i < Mdl::NS; ++i) {
             vs[i] = R(0);
@@ -194,32 +306,33 @@ struct ValueFn {
 //   K = -Quu^-1 Qux,  k = -Quu^-1 qu                         (:246-247)
 //   V = Qxx + Qux^T K + K^T Qux + (K^T Quu) K                (:248-251)
 //   v = qx  + Qux^T k + K^T qu  + (K^T Quu) k                (:252-255)
-// with the products restricted to the structurally non-zero entries (see ilqr_models.cuh).
+// with the products restricted to the structurally non-zero entries (see ilqr_models.cuh)
+// and the symmetric blocks (Qxx, V) formed in their upper triangle only.
 template <class Mdl, class R>
 CRL_HD void riccati_step(const R* xu, const R* p, ValueFn<Mdl, R>& vf, R (&Kout)[Mdl::M][Mdl::NS], R (&kout)[Mdl::M]) {
     constexpr int NS = Mdl::NS, NO = Mdl::NO, N = Mdl::N, M = Mdl::M;
     R A[NS][NS], B[NS][M], G[NO][NS];
-    Mdl::template jac<R>(xu, A, B, G);
+    model_jac<Mdl, R>(xu, A, B, G);
 
     // MA = A^T Vss (NS x NS), MB = B^T Vss (M x NS): sums over l ascending
     R MA[NS][NS], MB[M][NS];
     CRL_UNROLL for (int i = 0; i < NS; ++i)
         CRL_UNROLL for (int k = 0; k < NS; ++k) {
             R acc = R(0); bool have = false;
-            CRL_UNROLL for (int l = 0; l < NS; ++l) acc_kind(acc, have, vf.Vss[l][k], Mdl::akind(l, i), Mdl::aconst(l, i), A[l][i]);
+            CRL_UNROLL for (int l = 0; l < NS; ++l) acc_kind(acc, have, vf.V(l, k), Mdl::akind(l, i), Mdl::aconst(l, i), A[l][i]);
             MA[i][k] = acc;
         }
     CRL_UNROLL for (int a = 0; a < M; ++a)
         CRL_UNROLL for (int k = 0; k < NS; ++k) {
             R acc = R(0); bool have = false;
-            CRL_UNROLL for (int l = 0; l < NS; ++l) acc_kind(acc, have, vf.Vss[l][k], Mdl::bkind(l, a), Mdl::bconst(l, a), B[l][a]);
+            CRL_UNROLL for (int l = 0; l < NS; ++l) acc_kind(acc, have, vf.V(l, k), Mdl::bkind(l, a), Mdl::bconst(l, a), B[l][a]);
             MB[a][k] = acc;
         }
 
-    // Q blocks
+    // Q blocks (Qss: upper triangle)
     R Qss[NS][NS], Qus[M][NS + 1], Quu[M][M], qs[NS];     // Qus carries qu as extra column NS
     CRL_UNROLL for (int i = 0; i < NS; ++i)
-        CRL_UNROLL for (int j = 0; j < NS; ++j) {
+        CRL_UNROLL for (int j = i; j < NS; ++j) {
             R acc = R(0); bool have = false;
             CRL_UNROLL for (int k = 0; k < NS; ++k) acc_kind(acc, have, MA[i][k], Mdl::akind(k, j), Mdl::aconst(k, j), A[k][j]);
             CRL_UNROLL for (int y = 0; y < NO; ++y)
@@ -288,19 +401,16 @@ CRL_HD void riccati_step(const R* xu, const R* p, ValueFn<Mdl, R>& vf, R (&Kout)
         }
         vf.vs[i] = ((qs[i] + t1) + t2) + t3;
     }
-    // V = ((Qss + S) + S^T) + W K,  S = Qus^T K  (K^T Qus is S^T bit for bit)
-    R S[NS][NS];
+    // V = ((Qss + S) + S^T) + W K with S = Qus^T K, upper triangle only
     CRL_UNROLL for (int i = 0; i < NS; ++i)
-        CRL_UNROLL for (int j = 0; j < NS; ++j) {
-            R acc = Qus[0][i] * Kout[0][j];
-            CRL_UNROLL for (int a = 1; a < M; ++a) acc = fmadd(Qus[a][i], Kout[a][j], acc);
-            S[i][j] = acc;
-        }
-    CRL_UNROLL for (int i = 0; i < NS; ++i)
-        CRL_UNROLL for (int j = 0; j < NS; ++j) {
-            R r = W[i][0] * Kout[0][j];
-            CRL_UNROLL for (int b = 1; b < M; ++b) r = fmadd(W[i][b], Kout[b][j], r);
-            vf.Vss[i][j] = ((Qss[i][j] + S[i][j]) + S[j][i]) + r;
+        CRL_UNROLL for (int j = i; j < NS; ++j) {
+            R sij = Qus[0][i] * Kout[0][j], sji = Qus[0][j] * Kout[0][i], r = W[i][0] * Kout[0][j];
+            CRL_UNROLL for (int a = 1; a < M; ++a) {
+                sij = fmadd(Qus[a][i], Kout[a][j], sij);
+                sji = fmadd(Qus[a][j], Kout[a][i], sji);
+                r = fmadd(W[i][a], Kout[a][j], r);
+            }
+            vf.Vss[i][j] = ((Qss[i][j] + sij) + sji) + r;
         }
     // output block: Vyy <- Cyy, vy <- c_y(x_t)
     CRL_UNROLL for (int y = 0; y < NO; ++y) {
@@ -320,6 +430,7 @@ CRL_HD void backward_fused(View<R, Mdl::D, SCX> X, const ParamRef<R>& prm, int T
     vf.clear();
     for (int t = T - 1; t >= 0; --t) {
         R xu[D], p[P], Kt[M][NS], kt[M];
+        if (t > 0) X.prefetch(t - 1);           // row t-1 travels from HBM while row t is processed
         const R* row = X.row(t);
         CRL_UNROLL for (int i = 0; i < D; ++i) xu[i] = X.ld(row, i);
         CRL_UNROLL for (int i = 0; i < P; ++i) p[i] = prm.get(t, i);
@@ -338,7 +449,7 @@ template <class Mdl, class R>
 CRL_HD void derivs_dense(const R* xu, const R* p, R* F, R* c, R* C) {
     constexpr int NS = Mdl::NS, NO = Mdl::NO, N = Mdl::N, M = Mdl::M, D = Mdl::D;
     R A[NS][NS], B[NS][M], G[NO][NS];
-    Mdl::template jac<R>(xu, A, B, G);
+    model_jac<Mdl, R>(xu, A, B, G);
     for (int i = 0; i < N * D; ++i) F[i] = R(0);
     CRL_UNROLL for (int i = 0; i < NS; ++i) {
         CRL_UNROLL for (int j = 0; j < NS; ++j) {

@@ -27,6 +27,7 @@ namespace crl {
 
 constexpr int kBlock = 128;       // threads per CTA (4 warps)
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kLsChunk = 4;       // step sizes evaluated per pass of the line search
 
 template <class R>
 struct ProblemDev {
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__(kBlock, MINB) solve_kernel(SolveArgs<R> a) {
     bool exhausted = false;      // warp-uniform: the global queue is empty
     long long traj = -1;         // this lane's trajectory, -1 = idle
     int it = 0;
+    int pred = 0;                // step index this lane's trajectory accepted last (line-search guess)
     double J_last = 0.0;
     ParamRef<R> prm{a.pb.params, 0};
 
@@ -211,6 +213,7 @@ __global__ void __launch_bounds__(kBlock, MINB) solve_kernel(SolveArgs<R> a) {
                 if (idx < a.pb.B) {
                     traj = idx;
                     it = 0;
+                    pred = 0;
                     J_last = a.J_init ? a.J_init[idx] : (double)INFINITY;
                     prm = a.pb.prm(idx);
                     const View<R, D, 32> Xc = cur ? Xbuf1 : Xbuf0;
@@ -228,24 +231,65 @@ __global__ void __launch_bounds__(kBlock, MINB) solve_kernel(SolveArgs<R> a) {
         // ---- backward pass: K, k for every active lane
         if (active) backward_fused<Mdl, R, NS, 32, 32>(Xc, prm, T, Kv, kv);
 
-        // ---- line search: first improving alpha = 1, g, g^2, ...  (lanes drop out as they accept)
+        // ---- line search: first improving alpha = 1, g, g^2, ...
+        // Candidates are evaluated kLsChunk at a time in one pass over X, K, k (rollout_multi);
+        // each lane keeps the candidate it expects to win (`pred`, the index accepted last
+        // time) and re-materialises the winner with one more rollout only if it guessed wrong.
         bool accepted = false;
-        double J_new = J_last, alpha = 1.0;
+        double J_new = J_last, alpha = 1.0, alpha_taken = 1.0;
         int taken = -1;
+        bool replay = false;
         const int tries = (a.op.ls_method == CRL_LS_NONE) ? 1 : a.op.max_ls;
-        for (int ls = 0; ls < tries; ++ls) {
+        const bool feas = a.op.ls_method == CRL_LS_FEASIBILITY;
+        int a0 = 0;
+        while (a0 < tries) {
             const bool pending = active && !accepted;
             if (!__any_sync(kFull, pending)) break;
-            if (pending) {
-                const double Jt = rollout_closed<Mdl, R, NS, 32, 32, 32>(Xc, Kv, kv, (R)alpha, prm, a.pb.ub, T, Xn);
-                if (a.op.ls_method == CRL_LS_NONE || ls_accept(Jt, J_last, a.op.ls_method == CRL_LS_FEASIBILITY)) {
-                    accepted = true;
-                    J_new = Jt;
-                    taken = ls;
+            // a warp whose pending lanes all expect alpha = 1 to be accepted tries it alone first
+            const bool wide = (tries - a0 >= 2) && (a0 > 0 || __any_sync(kFull, pending && pred > 0));
+            if (wide) {
+                R al[kLsChunk];
+                double ald[kLsChunk];
+#pragma unroll
+                for (int c = 0; c < kLsChunk; ++c) {
+                    ald[c] = alpha;
+                    al[c] = (R)alpha;
+                    alpha = alpha * a.op.gamma;
                 }
+                if (pending) {
+                    int keep = pred - a0;
+                    keep = keep < 0 ? 0 : (keep > kLsChunk - 1 ? kLsChunk - 1 : keep);
+                    double Jc[kLsChunk];
+                    rollout_multi<Mdl, R, kLsChunk, NS, 32, 32, 32>(Xc, Kv, kv, al, prm, a.pb.ub, T, keep, Xn, Jc);
+#pragma unroll
+                    for (int c = 0; c < kLsChunk; ++c) {
+                        if (!accepted && a0 + c < tries && ls_accept(Jc[c], J_last, feas)) {
+                            accepted = true;
+                            J_new = Jc[c];
+                            taken = a0 + c;
+                            alpha_taken = ald[c];
+                            replay = (c != keep);
+                        }
+                    }
+                }
+                a0 += kLsChunk;
+            } else {
+                if (pending) {
+                    const double Jt = rollout_closed<Mdl, R, NS, 32, 32, 32>(Xc, Kv, kv, (R)alpha, prm, a.pb.ub, T, Xn);
+                    if (a.op.ls_method == CRL_LS_NONE || ls_accept(Jt, J_last, feas)) {
+                        accepted = true;
+                        J_new = Jt;
+                        taken = a0;
+                    }
+                }
+                alpha = alpha * a.op.gamma;
+                a0 += 1;
             }
-            alpha = alpha * a.op.gamma;
         }
+        if (__any_sync(kFull, replay)) {
+            if (replay) rollout_closed<Mdl, R, NS, 32, 32, 32>(Xc, Kv, kv, (R)alpha_taken, prm, a.pb.ub, T, Xn);
+        }
+        if (accepted) pred = taken;
 
         // ---- stop test, bookkeeping, retirement
         bool finished = false;
@@ -263,6 +307,7 @@ __global__ void __launch_bounds__(kBlock, MINB) solve_kernel(SolveArgs<R> a) {
                 if (a.X_out) {
                     const View<R, D, 32> src = accepted ? Xn : Xc;
                     R* dst = a.X_out + traj * T * D;
+#pragma unroll 4
                     for (int t = 0; t < T; ++t) {
                         const R* row = src.row(t);
 #pragma unroll
@@ -276,6 +321,7 @@ __global__ void __launch_bounds__(kBlock, MINB) solve_kernel(SolveArgs<R> a) {
         const bool carry = active && !finished && !accepted;
         if (__any_sync(kFull, carry)) {
             if (carry) {
+#pragma unroll 8
                 for (int t = 0; t < T; ++t) {
                     const R* src = Xc.row(t);
                     R* dst = Xn.row(t);
@@ -333,6 +379,7 @@ static int check_problem(const crl_problem_t* p) {
 static int check_opts(const crl_solver_opts_t* o) {
     if (!o) return CRL_ERR_BAD_ARGUMENT;
     if (o->max_iter < 0 || o->max_line_search < 0) return CRL_ERR_BAD_ARGUMENT;
+    if (o->reserved != 0 && (o->reserved < 2 || o->reserved > 4)) return CRL_ERR_BAD_ARGUMENT;
     if (o->line_search_method < CRL_LS_VANILLA || o->line_search_method > CRL_LS_NONE) return CRL_ERR_BAD_ARGUMENT;
     if (o->stopping_method < CRL_STOP_RELATIVE || o->stopping_method > CRL_STOP_VANILLA) return CRL_ERR_BAD_ARGUMENT;
     return CRL_OK;
@@ -392,17 +439,38 @@ template <class R> struct SolveCfg;
 template <> struct SolveCfg<double> { static constexpr int MINB = 2; };
 template <> struct SolveCfg<float> { static constexpr int MINB = 4; };
 
-template <class Mdl, class R>
-static int solve_grid(int requested) {
+template <class Mdl, class R, int MINB>
+static int solve_grid_v(int requested) {
     if (requested > 0) return requested;
     int dev = 0, sms = 0, per_sm = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel<Mdl, R, SolveCfg<R>::MINB>, kBlock, 0) !=
-        cudaSuccess)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel<Mdl, R, MINB>, kBlock, 0) != cudaSuccess)
         return -1;
     if (per_sm < 1) per_sm = 1;
     return sms * per_sm;
+}
+
+// occupancy variant: opts->reserved = resident CTAs per SM to compile for (0 = default)
+template <class Mdl, class R>
+static int solve_grid(int requested, int variant) {
+    const int v = variant > 0 ? variant : SolveCfg<R>::MINB;
+    switch (v) {
+        case 2: return solve_grid_v<Mdl, R, 2>(requested);
+        case 3: return solve_grid_v<Mdl, R, 3>(requested);
+        case 4: return solve_grid_v<Mdl, R, 4>(requested);
+        default: return -1;
+    }
+}
+
+template <class Mdl, class R>
+static void solve_launch(int variant, int grid, cudaStream_t s, const SolveArgs<R>& a) {
+    const int v = variant > 0 ? variant : SolveCfg<R>::MINB;
+    switch (v) {
+        case 2: solve_kernel<Mdl, R, 2><<<grid, kBlock, 0, s>>>(a); break;
+        case 3: solve_kernel<Mdl, R, 3><<<grid, kBlock, 0, s>>>(a); break;
+        default: solve_kernel<Mdl, R, 4><<<grid, kBlock, 0, s>>>(a); break;
+    }
 }
 
 }  // namespace crl
@@ -566,7 +634,7 @@ size_t crl_solve_workspace_bytes(const crl_problem_t* prob, const crl_solver_opt
     if (check_problem(prob) || check_opts(opts)) return 0;
     long long reals = 0;
     int grid = 0;
-    CRL_DISPATCH(prob->model, prob->dtype, (reals = slot_reals<Mdl>(prob->horizon), grid = solve_grid<Mdl, R>(opts->grid_blocks)));
+    CRL_DISPATCH(prob->model, prob->dtype, (reals = slot_reals<Mdl>(prob->horizon), grid = solve_grid<Mdl, R>(opts->grid_blocks, opts->reserved)));
     if (grid <= 0) return 0;
     const size_t elem = prob->dtype == CRL_F64 ? 8 : 4;
     const size_t slots = (size_t)grid * (kBlock / 32);
@@ -609,8 +677,8 @@ int crl_solve(const crl_problem_t* prob, const crl_solver_opts_t* opts, const vo
         a.counter = (unsigned long long*)workspace;
         a.ws = (R*)((char*)workspace + 256);
         a.slot_elems = slot_reals<Mdl>(prob->horizon);
-        const int grid = solve_grid<Mdl, R>(opts->grid_blocks);
-        solve_kernel<Mdl, R, SolveCfg<R>::MINB><<<grid, kBlock, 0, s>>>(a);
+        const int grid = solve_grid<Mdl, R>(opts->grid_blocks, opts->reserved);
+        solve_launch<Mdl, R>(opts->reserved, grid, s, a);
     });
     return cuda_status(cudaGetLastError());
 }

@@ -49,21 +49,25 @@ struct KinematicArm {
     CRL_HD static constexpr double u_lo(int) { return -100.0; }
     CRL_HD static constexpr double u_hi(int) { return 100.0; }
 
-    // x_{t+1} = f(x_t, u_t); xu = (s, y, u)
+    // angles whose sin/cos one time step needs: the cumulative joint angles
+    static constexpr int NANG = J;
     template <class R>
-    CRL_HD static void step(const R* xu, R* xn) {
+    CRL_HD static void angles(const R* xu, R* ang) {
+        ang[0] = xu[0];
+        CRL_UNROLL for (int j = 1; j < J; ++j) ang[j] = ang[j - 1] + xu[2 * j];
+    }
+
+    // x_{t+1} = f(x_t, u_t); xu = (s, y, u); sn/cs = sin/cos of angles(xu)
+    template <class R>
+    CRL_HD static void step_trig(const R* xu, const R* sn, const R* cs, R* xn) {
         CRL_UNROLL for (int j = 0; j < J; ++j) {
             xn[2 * j] = xu[2 * j] + R(kH) * xu[2 * j + 1];
             xn[2 * j + 1] = xu[2 * j + 1] + R(kH) * xu[N + j];
         }
-        R ang = xu[0], ex, ey, s, c;
-        sincos_(ang, &s, &c);
-        ex = s; ey = c;                                      // l1 = 1: sympy prints sin(x0), not 1*sin(x0)
+        R ex = sn[0], ey = cs[0];                            // l1 = 1: sympy prints sin(x0), not 1*sin(x0)
         CRL_UNROLL for (int j = 1; j < J; ++j) {
-            ang = ang + xu[2 * j];
-            sincos_(ang, &s, &c);
-            ex = ex + R(link(j)) * s;
-            ey = ey + R(link(j)) * c;
+            ex = ex + R(link(j)) * sn[j];
+            ey = ey + R(link(j)) * cs[j];
         }
         xn[NS] = ex;
         xn[NS + 1] = ey;
@@ -71,15 +75,8 @@ struct KinematicArm {
 
     // Variable Jacobian entries: G[0][2i] = sum_{j>=i} l_j cos(a_j), G[1][2i] = -sum_{j>=i} l_j sin(a_j)
     template <class R>
-    CRL_HD static void jac(const R* xu, R (*A)[NS], R (*B)[M], R (*G)[NS]) {
-        (void)A; (void)B;
-        R sn[J], cs[J];
-        R ang = xu[0];
-        sincos_(ang, &sn[0], &cs[0]);
-        CRL_UNROLL for (int j = 1; j < J; ++j) {
-            ang = ang + xu[2 * j];
-            sincos_(ang, &sn[j], &cs[j]);
-        }
+    CRL_HD static void jac_trig(const R* xu, const R* sn, const R* cs, R (*A)[NS], R (*B)[M], R (*G)[NS]) {
+        (void)xu; (void)A; (void)B;
         CRL_UNROLL for (int i = 0; i < J; ++i) {
             // left-to-right sums as printed: cos(a_i)*l_i + l_{i+1} cos(a_{i+1}) + ...
             R gc = (i == 0) ? cs[0] : R(link(i)) * cs[i];
@@ -93,6 +90,22 @@ struct KinematicArm {
         }
     }
 };
+
+// step / jac with the trigonometry evaluated in place (single-candidate callers)
+template <class Mdl, class R>
+CRL_HD void model_step(const R* xu, R* xn) {
+    R ang[Mdl::NANG], sn[Mdl::NANG], cs[Mdl::NANG];
+    Mdl::template angles<R>(xu, ang);
+    sincos_batch<Mdl::NANG, R>(ang, sn, cs);
+    Mdl::template step_trig<R>(xu, sn, cs, xn);
+}
+template <class Mdl, class R>
+CRL_HD void model_jac(const R* xu, R (*A)[Mdl::NS], R (*B)[Mdl::M], R (*G)[Mdl::NS]) {
+    R ang[Mdl::NANG], sn[Mdl::NANG], cs[Mdl::NANG];
+    Mdl::template angles<R>(xu, ang);
+    sincos_batch<Mdl::NANG, R>(ang, sn, cs);
+    Mdl::template jac_trig<R>(xu, sn, cs, A, B, G);
+}
 
 struct TwoLink : KinematicArm<2> {
     static constexpr int ID = 0;
@@ -150,11 +163,17 @@ struct RoboticArm {
     template <class R>
     struct Terms { R s, c, s1, c1, s2, c2, id, R1, R2, a1, a2; };
 
+    static constexpr int NANG = 3;                           // delta, th1, th2
     template <class R>
-    CRL_HD static void terms(const R* xu, Terms<R>& t) {
-        sincos_(xu[0] - xu[2], &t.s, &t.c);
-        sincos_(xu[0], &t.s1, &t.c1);
-        sincos_(xu[2], &t.s2, &t.c2);
+    CRL_HD static void angles(const R* xu, R* ang) {
+        ang[0] = xu[0] - xu[2];
+        ang[1] = xu[0];
+        ang[2] = xu[2];
+    }
+
+    template <class R>
+    CRL_HD static void terms(const R* xu, const R* sn, const R* cs, Terms<R>& t) {
+        t.s = sn[0]; t.c = cs[0]; t.s1 = sn[1]; t.c1 = cs[1]; t.s2 = sn[2]; t.c2 = cs[2];
         R den = R(4.0) * (t.c * t.c) - R(kden);
         t.id = R(1.0) / den;
         t.R1 = xu[6] + (R(-2.0) * (xu[3] * xu[3]) * t.s + R(24.5) * t.s1);
@@ -165,9 +184,9 @@ struct RoboticArm {
     }
 
     template <class R>
-    CRL_HD static void step(const R* xu, R* xn) {
+    CRL_HD static void step_trig(const R* xu, const R* sn, const R* cs, R* xn) {
         Terms<R> t;
-        terms(xu, t);
+        terms(xu, sn, cs, t);
         xn[0] = xu[0] + R(kH) * xu[1];
         xn[1] = xu[1] + t.a1;
         xn[2] = xu[2] + R(kH) * xu[3];
@@ -177,9 +196,9 @@ struct RoboticArm {
     }
 
     template <class R>
-    CRL_HD static void jac(const R* xu, R (*A)[NS], R (*B)[M], R (*G)[NS]) {
+    CRL_HD static void jac_trig(const R* xu, const R* sn, const R* cs, R (*A)[NS], R (*B)[M], R (*G)[NS]) {
         Terms<R> t;
-        terms(xu, t);
+        terms(xu, sn, cs, t);
         const R w1 = xu[1], w2 = xu[3], s = t.s, c = t.c, id = t.id;
         const R hc = R(0.02) * c, hs = R(0.02) * s;
         // d den / d th1 = -8 c s ; d den / d th2 = +8 c s

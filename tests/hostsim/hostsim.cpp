@@ -65,19 +65,39 @@ struct Sim {
         View<R, M, 1> kv{kb.data()};
         rollout_open<Mdl, R, 1>(x0, 1, u0, M, prm, ub, T, X0);
         double J_last = J_init;
-        int it = 0;
+        int it = 0, pred = 0;
         while (true) {
             View<R, D, 1> Xc = cur ? X1 : X0, Xn = cur ? X0 : X1;
             backward_fused<Mdl, R, NS, 1, 1>(Xc, prm, T, Kv, kv);
-            bool accepted = false;
-            double J_new = J_last, alpha = 1.0;
+            bool accepted = false, replay = false;
+            double J_new = J_last, alpha = 1.0, alpha_taken = 1.0;
             int taken = -1;
             const int tries = (ls_method == 2) ? 1 : max_ls;
-            for (int ls = 0; ls < tries && !accepted; ++ls) {
-                const double Jt = rollout_closed<Mdl, R, NS, 1, 1, 1>(Xc, Kv, kv, (R)alpha, prm, ub, T, Xn);
-                if (ls_method == 2 || ls_accept(Jt, J_last, ls_method == 1)) { accepted = true; J_new = Jt; taken = ls; }
-                alpha = alpha * gamma;
+            constexpr int CH = 4;                       // = kLsChunk of ilqr_kernels.cu
+            int a0 = 0;
+            while (a0 < tries && !accepted) {
+                const bool wide = (tries - a0 >= 2) && (a0 > 0 || pred > 0);
+                if (wide) {
+                    R al[CH];
+                    double ald[CH], Jc[CH];
+                    for (int c = 0; c < CH; ++c) { ald[c] = alpha; al[c] = (R)alpha; alpha = alpha * gamma; }
+                    int keep = pred - a0;
+                    keep = keep < 0 ? 0 : (keep > CH - 1 ? CH - 1 : keep);
+                    rollout_multi<Mdl, R, CH, NS, 1, 1, 1>(Xc, Kv, kv, al, prm, ub, T, keep, Xn, Jc);
+                    for (int c = 0; c < CH; ++c)
+                        if (!accepted && a0 + c < tries && ls_accept(Jc[c], J_last, ls_method == 1)) {
+                            accepted = true; J_new = Jc[c]; taken = a0 + c; alpha_taken = ald[c]; replay = (c != keep);
+                        }
+                    a0 += CH;
+                } else {
+                    const double Jt = rollout_closed<Mdl, R, NS, 1, 1, 1>(Xc, Kv, kv, (R)alpha, prm, ub, T, Xn);
+                    if (ls_method == 2 || ls_accept(Jt, J_last, ls_method == 1)) { accepted = true; J_new = Jt; taken = a0; }
+                    alpha = alpha * gamma;
+                    a0 += 1;
+                }
             }
+            if (replay) rollout_closed<Mdl, R, NS, 1, 1, 1>(Xc, Kv, kv, (R)alpha_taken, prm, ub, T, Xn);
+            if (accepted) pred = taken;
             const bool stop = stop_test(J_new, J_last, criterion, stop_method == 0);
             J_last = J_new;
             if (J_trace) J_trace[it] = J_new;

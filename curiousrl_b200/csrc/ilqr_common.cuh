@@ -148,25 +148,6 @@ struct View {
     CRL_HD R* row(int t) const { return base + (size_t)t * (W * SC); }
     CRL_HD static R ld(const R* row, int c) { return row[c * SC]; }
     CRL_HD static void st(R* row, int c, R v) { row[c * SC] = v; }
-    // Warp-tile layout only: pull time step t's block (W*32 reals, contiguous) into L1 ahead of
-    // use.  Each lane touches different 128-byte lines, so a whole block costs 1-2 instructions
-    // and no registers; the later loads then hit L1 instead of waiting on HBM.
-    CRL_HD void prefetch(int t) const {
-#if defined(__CUDA_ARCH__)
-        if (SC == 32) {
-            const int lane = threadIdx.x & 31;
-            const char* blk = reinterpret_cast<const char*>(row(t) - lane);
-            constexpr int kBytes = W * 32 * (int)sizeof(R);
-#pragma unroll
-            for (int off = 0; off < kBytes; off += 32 * 128) {
-                const int o = off + lane * 128;
-                if (o < kBytes) asm volatile("prefetch.global.L1 [%0];" ::"l"(blk + o));
-            }
-        }
-#else
-        (void)t;
-#endif
-    }
 };
 
 }  // namespace crl

@@ -36,10 +36,11 @@ CRL_HD double step_cost(const R* xu, const ParamRef<R>& prm, int t) {
 }
 
 // Run-time action bounds (lets RoboticArm(is_with_constraints=False) share the device model).
+// The clamp is applied unconditionally, also against +-inf, exactly as the reference does
+// (min(max(-inf, u), inf)); keeping it branch-free also keeps a time step one basic block.
 template <class R>
 struct Bounds {
     R lo, hi;          // same box for every action, as in all three scenarios
-    bool active;       // false -> bounds are +-inf, clamps skipped
 };
 
 // -----------------------------------------------------------------------------------------
@@ -58,7 +59,7 @@ CRL_HD double rollout_open(const R* x0, int sx0, const R* U, int su_t, const Par
     for (int t = 0; t < T; ++t) {
         const bool last = (t == T - 1);
         if (!last) model_step<Mdl, R>(xu, xn);            // from the unclamped row
-        if (!last && ub.active) {
+        if (!last) {
             CRL_UNROLL for (int a = 0; a < M; ++a) xu[N + a] = clamp_(xu[N + a], ub.lo, ub.hi);
         }
         R* row = X.row(t);
@@ -121,7 +122,7 @@ CRL_HD double rollout_closed(View<R, Mdl::D, SCX> Xold, View<R, Mdl::M * KN, SCK
             CRL_UNROLL for (int j = 1; j < KN; ++j) acc = fmadd(K_c[a * KN + j], dx[j], acc);
             R du = acc + alpha * k_c[a];
             R u = uo_c[a] + du;
-            if (ub.active) u = clamp_(u, ub.lo, ub.hi);
+            u = clamp_(u, ub.lo, ub.hi);
             xu[N + a] = u;
         }
         R* row = Xnew.row(t);
@@ -144,9 +145,9 @@ CRL_HD double rollout_closed(View<R, Mdl::D, SCX> Xold, View<R, Mdl::M * KN, SCK
 // and shared by all candidates (this is what makes the line search move its algorithmic bytes
 // only), and the NA independent rollouts give each lane NA-way instruction-level parallelism.
 // Per candidate the arithmetic is exactly rollout_closed's, so every J[a] is bit-identical to
-// a separate single-alpha call.  Only the candidate with index `keep` (per lane, -1 = none)
-// is written to Xnew; a different winner is re-materialised by one rollout_closed call.
-template <class Mdl, class R, int NA, int KN, int SCX, int SCK, int SCXN>
+// a separate single-alpha call.  Only the candidate with index `keep` (per lane) is written
+// to Xnew (STORE = false: none); a different winner is re-materialised by one rollout_closed call.
+template <class Mdl, class R, int NA, int KN, int SCX, int SCK, int SCXN, bool STORE = true>
 CRL_HD void rollout_multi(View<R, Mdl::D, SCX> Xold, View<R, Mdl::M * KN, SCK> Kv, View<R, Mdl::M, SCK> kv,
                           const R (&alpha)[NA], const ParamRef<R>& prm, const Bounds<R>& ub, int T, int keep,
                           View<R, Mdl::D, SCXN> Xnew, double (&J)[NA]) {
@@ -164,11 +165,6 @@ CRL_HD void rollout_multi(View<R, Mdl::D, SCX> Xold, View<R, Mdl::M * KN, SCK> K
         const R* xo = Xold.row(t);
         const R* Kr = Kv.row(t);
         const R* kr = kv.row(t);
-        if (t + 1 < T - 1) {                 // next step's inputs start their trip from HBM now
-            Xold.prefetch(t + 1);
-            Kv.prefetch(t + 1);
-            kv.prefetch(t + 1);
-        }
         R xo_c[KN], uo_c[M], K_c[M * KN], k_c[M];
         CRL_UNROLL for (int j = 0; j < KN; ++j) xo_c[j] = Xold.ld(xo, j);
         CRL_UNROLL for (int a = 0; a < M; ++a) uo_c[a] = Xold.ld(xo, N + a);
@@ -182,11 +178,11 @@ CRL_HD void rollout_multi(View<R, Mdl::D, SCX> Xold, View<R, Mdl::M * KN, SCK> K
                 CRL_UNROLL for (int j = 1; j < KN; ++j) acc = fmadd(K_c[a * KN + j], dx[j], acc);
                 R du = acc + alpha[c] * k_c[a];
                 R u = uo_c[a] + du;
-                if (ub.active) u = clamp_(u, ub.lo, ub.hi);
+                u = clamp_(u, ub.lo, ub.hi);
                 xu[c][N + a] = u;
             }
         }
-        if (keep >= 0) {
+        if (STORE) {
             R* row = Xnew.row(t);
             CRL_UNROLL for (int i = 0; i < D; ++i) {
                 R v = xu[0][i];
@@ -213,7 +209,7 @@ CRL_HD void rollout_multi(View<R, Mdl::D, SCX> Xold, View<R, Mdl::M * KN, SCK> K
         }
         J[c] = J[c] + step_cost<Mdl, R>(xu[c], prm, T - 1);
     }
-    if (keep >= 0) {
+    if (STORE) {
         R* row = Xnew.row(T - 1);
         CRL_UNROLL for (int i = 0; i < D; ++i) {
             R v = xu[0][i];
@@ -430,7 +426,6 @@ CRL_HD void backward_fused(View<R, Mdl::D, SCX> X, const ParamRef<R>& prm, int T
     vf.clear();
     for (int t = T - 1; t >= 0; --t) {
         R xu[D], p[P], Kt[M][NS], kt[M];
-        if (t > 0) X.prefetch(t - 1);           // row t-1 travels from HBM while row t is processed
         const R* row = X.row(t);
         CRL_UNROLL for (int i = 0; i < D; ++i) xu[i] = X.ld(row, i);
         CRL_UNROLL for (int i = 0; i < P; ++i) p[i] = prm.get(t, i);

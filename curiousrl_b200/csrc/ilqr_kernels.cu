@@ -27,6 +27,7 @@ namespace crl {
 
 constexpr int kBlock = 128;       // threads per CTA (4 warps)
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kCoopMax = 6;        // a drained warp with <= this many live trajectories works on them cooperatively
 constexpr int kLsChunk = 4;       // step sizes evaluated per pass of the line search
 
 template <class R>
@@ -232,62 +233,118 @@ __global__ void __launch_bounds__(kBlock, MINB) solve_kernel(SolveArgs<R> a) {
         if (active) backward_fused<Mdl, R, NS, 32, 32>(Xc, prm, T, Kv, kv);
 
         // ---- line search: first improving alpha = 1, g, g^2, ...
-        // Candidates are evaluated kLsChunk at a time in one pass over X, K, k (rollout_multi);
-        // each lane keeps the candidate it expects to win (`pred`, the index accepted last
-        // time) and re-materialises the winner with one more rollout only if it guessed wrong.
         bool accepted = false;
-        double J_new = J_last, alpha = 1.0, alpha_taken = 1.0;
+        double J_new = J_last;
         int taken = -1;
-        bool replay = false;
         const int tries = (a.op.ls_method == CRL_LS_NONE) ? 1 : a.op.max_ls;
         const bool feas = a.op.ls_method == CRL_LS_FEASIBILITY;
-        int a0 = 0;
-        while (a0 < tries) {
-            const bool pending = active && !accepted;
-            if (!__any_sync(kFull, pending)) break;
-            // a warp whose pending lanes all expect alpha = 1 to be accepted tries it alone first
-            const bool wide = (tries - a0 >= 2) && (a0 > 0 || __any_sync(kFull, pending && pred > 0));
-            if (wide) {
-                R al[kLsChunk];
-                double ald[kLsChunk];
-#pragma unroll
-                for (int c = 0; c < kLsChunk; ++c) {
-                    ald[c] = alpha;
-                    al[c] = (R)alpha;
-                    alpha = alpha * a.op.gamma;
+        const unsigned act = __ballot_sync(kFull, active);
+        if (exhausted && __popc(act) <= kCoopMax) {
+            // Straggler mode (queue empty, few trajectories left in this warp): the line search of
+            // one trajectory at a time is spread over the idle lanes, one step size per lane, so a
+            // whole line search costs one rollout of latency instead of up to max_line_search.
+            // Candidate arithmetic is rollout_closed's, hence results do not depend on the mode.
+            __syncwarp();                                   // K, k of the owners are read by other lanes below
+            const unsigned idle = ~act;
+            const int n_idle = __popc(idle);
+            const int my_rank = __popc(idle & ((1u << lane) - 1u));
+            const bool is_idle = (idle >> lane) & 1u;
+            R* const ws0 = wsb - lane;                      // column 0 of this warp's tiles
+            for (unsigned m = act; m != 0u; m &= m - 1u) {
+                const int owner = __ffs(m) - 1;
+                const double Jl_o = __shfl_sync(kFull, J_last, owner);
+                const unsigned long long pp = __shfl_sync(kFull, (unsigned long long)(uintptr_t)prm.ptr, owner);
+                const ParamRef<R> prm_o{(const R*)(uintptr_t)pp, __shfl_sync(kFull, prm.stride_t, owner)};
+                const View<R, D, 32> Xc_o{ws0 + (cur ? (size_t)T * D * 32 : 0) + owner};
+                const View<R, M * NS, 32> Kv_o{ws0 + (size_t)2 * T * D * 32 + owner};
+                const View<R, M, 32> kv_o{ws0 + (size_t)2 * T * D * 32 + (size_t)T * M * NS * 32 + owner};
+                int win_lane = -1, win_idx = -1;
+                double J_win = Jl_o;
+                for (int a0 = 0; a0 < tries && win_lane < 0; a0 += n_idle) {
+                    const int idx = a0 + my_rank;
+                    const bool work = is_idle && idx < tries;
+                    double Jt = 0.0;
+                    bool ok = false;
+                    if (work) {
+                        double al = 1.0;
+                        for (int i = 0; i < idx; ++i) al = al * a.op.gamma;
+                        Jt = rollout_closed<Mdl, R, NS, 32, 32, 32>(Xc_o, Kv_o, kv_o, (R)al, prm_o, a.pb.ub, T, Xn);
+                        ok = (a.op.ls_method == CRL_LS_NONE) || ls_accept(Jt, Jl_o, feas);
+                    }
+                    const unsigned okm = __ballot_sync(kFull, ok);
+                    if (okm != 0u) {
+                        win_lane = __ffs(okm) - 1;               // lowest idle lane = lowest step index
+                        win_idx = a0 + __popc(idle & ((1u << win_lane) - 1u));
+                        J_win = __shfl_sync(kFull, Jt, win_lane);
+                    }
                 }
-                if (pending) {
-                    int keep = pred - a0;
-                    keep = keep < 0 ? 0 : (keep > kLsChunk - 1 ? kLsChunk - 1 : keep);
-                    double Jc[kLsChunk];
-                    rollout_multi<Mdl, R, kLsChunk, NS, 32, 32, 32>(Xc, Kv, kv, al, prm, a.pb.ub, T, keep, Xn, Jc);
-#pragma unroll
+                __syncwarp();
+                if (win_lane >= 0) {
+                    // move the winning candidate from the helper's column to the owner's column of X_new
+                    R* const xn0 = Xn.base - lane;
+                    for (int e = lane; e < T * D; e += 32) xn0[(size_t)e * 32 + owner] = xn0[(size_t)e * 32 + win_lane];
+                }
+                __syncwarp();
+                if (lane == owner && win_lane >= 0) {
+                    accepted = true;
+                    J_new = J_win;
+                    taken = win_idx;
+                }
+            }
+        } else {
+            // Candidates are evaluated kLsChunk at a time in one pass over X, K, k (rollout_multi);
+            // each lane keeps the candidate it expects to win (`pred`, the index accepted last
+            // time) and re-materialises the winner with one more rollout only if it guessed wrong.
+            double alpha = 1.0, alpha_taken = 1.0;
+            bool replay = false;
+            int a0 = 0;
+            while (a0 < tries) {
+                const bool pending = active && !accepted;
+                if (!__any_sync(kFull, pending)) break;
+                // a warp whose pending lanes all expect alpha = 1 to be accepted tries it alone first
+                const bool wide = (tries - a0 >= 2) && (a0 > 0 || __any_sync(kFull, pending && pred > 0));
+                if (wide) {
+                    R al[kLsChunk];
+                    double ald[kLsChunk];
+    #pragma unroll
                     for (int c = 0; c < kLsChunk; ++c) {
-                        if (!accepted && a0 + c < tries && ls_accept(Jc[c], J_last, feas)) {
-                            accepted = true;
-                            J_new = Jc[c];
-                            taken = a0 + c;
-                            alpha_taken = ald[c];
-                            replay = (c != keep);
+                        ald[c] = alpha;
+                        al[c] = (R)alpha;
+                        alpha = alpha * a.op.gamma;
+                    }
+                    if (pending) {
+                        int keep = pred - a0;
+                        keep = keep < 0 ? 0 : (keep > kLsChunk - 1 ? kLsChunk - 1 : keep);
+                        double Jc[kLsChunk];
+                        rollout_multi<Mdl, R, kLsChunk, NS, 32, 32, 32>(Xc, Kv, kv, al, prm, a.pb.ub, T, keep, Xn, Jc);
+    #pragma unroll
+                        for (int c = 0; c < kLsChunk; ++c) {
+                            if (!accepted && a0 + c < tries && ls_accept(Jc[c], J_last, feas)) {
+                                accepted = true;
+                                J_new = Jc[c];
+                                taken = a0 + c;
+                                alpha_taken = ald[c];
+                                replay = (c != keep);
+                            }
                         }
                     }
-                }
-                a0 += kLsChunk;
-            } else {
-                if (pending) {
-                    const double Jt = rollout_closed<Mdl, R, NS, 32, 32, 32>(Xc, Kv, kv, (R)alpha, prm, a.pb.ub, T, Xn);
-                    if (a.op.ls_method == CRL_LS_NONE || ls_accept(Jt, J_last, feas)) {
-                        accepted = true;
-                        J_new = Jt;
-                        taken = a0;
+                    a0 += kLsChunk;
+                } else {
+                    if (pending) {
+                        const double Jt = rollout_closed<Mdl, R, NS, 32, 32, 32>(Xc, Kv, kv, (R)alpha, prm, a.pb.ub, T, Xn);
+                        if (a.op.ls_method == CRL_LS_NONE || ls_accept(Jt, J_last, feas)) {
+                            accepted = true;
+                            J_new = Jt;
+                            taken = a0;
+                        }
                     }
+                    alpha = alpha * a.op.gamma;
+                    a0 += 1;
                 }
-                alpha = alpha * a.op.gamma;
-                a0 += 1;
             }
-        }
-        if (__any_sync(kFull, replay)) {
-            if (replay) rollout_closed<Mdl, R, NS, 32, 32, 32>(Xc, Kv, kv, (R)alpha_taken, prm, a.pb.ub, T, Xn);
+            if (__any_sync(kFull, replay)) {
+                if (replay) rollout_closed<Mdl, R, NS, 32, 32, 32>(Xc, Kv, kv, (R)alpha_taken, prm, a.pb.ub, T, Xn);
+            }
         }
         if (accepted) pred = taken;
 
@@ -348,7 +405,6 @@ static ProblemDev<R> to_dev(const crl_problem_t* p) {
     d.T = p->horizon;
     d.ub.lo = (R)p->u_lo;
     d.ub.hi = (R)p->u_hi;
-    d.ub.active = !(p->u_lo == -INFINITY && p->u_hi == INFINITY);
     return d;
 }
 

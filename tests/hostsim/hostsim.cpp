@@ -20,7 +20,6 @@ struct Sim {
     static Bounds<R> bounds(double lo, double hi) {
         Bounds<R> b;
         b.lo = (R)lo; b.hi = (R)hi;
-        b.active = !(lo == -INFINITY && hi == INFINITY);
         return b;
     }
     static double rollout(const R* x0, const R* u0, const R* params, int stride_t, double lo, double hi, int T, R* X) {
@@ -160,6 +159,13 @@ struct Sim {
                                                conv_out, J_trace, alpha_trace)));                                      \
         return 0;                                                                                                      \
     }
+
+extern "C" void hs_sincos_f64(const double* x, int n, double* s, double* c) {
+    for (int i = 0; i < n; ++i) sincos_batch<1, double>(x + i, s + i, c + i);
+}
+extern "C" void hs_sincos_f32(const float* x, int n, float* s, float* c) {
+    for (int i = 0; i < n; ++i) sincos_batch<1, float>(x + i, s + i, c + i);
+}
 
 HS_API(f64, double)
 HS_API(f32, float)

@@ -159,3 +159,33 @@ def test_time_varying_target_and_given_actions(golden):
     r = hs.solve(x0, P, T, u0=U0)
     ref = orc.solve(prob, x0, P, U0)
     assert r["iters"] == ref["iters"] and abs(r["J"] - ref["J"]) <= 1e-9 * ref["J"] and rel(r["X"], ref["X"]) <= 1e-9
+
+
+def test_branch_free_sincos_accuracy():
+    """csrc sincos_batch (the kernels' replacement for the library sincos): ~1 ulp in double over the
+    working range (<= 1.5 ulp worst case), library fallback beyond it, NaN/Inf propagate."""
+    import ctypes
+    import mpmath
+    from hostsim import lib
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-4, 4, 4000), rng.uniform(-300, 300, 4000), rng.uniform(-9e4, 9e4, 2000),
+                        np.arange(-40, 41) * (np.pi / 4), [0.0, 1e-300, -1e-9, 2.5e5, -1e9, 1e22]])
+    s, c = np.zeros_like(x), np.zeros_like(x)
+    vp = ctypes.c_void_p
+    lib().hs_sincos_f64(x.ctypes.data_as(vp), len(x), s.ctypes.data_as(vp), c.ctypes.data_as(vp))
+    mpmath.mp.prec = 200
+    worst = 0.0
+    for xi, si, ci in zip(x, s, c):
+        for got, fn in ((si, mpmath.sin), (ci, mpmath.cos)):
+            ref = fn(mpmath.mpf(float(xi)))
+            ulp = np.spacing(abs(float(ref))) if float(ref) != 0 else 5e-324
+            worst = max(worst, abs(float((mpmath.mpf(float(got)) - ref) / ulp)))
+    assert worst <= 1.5, worst          # CUDA's own double sin/cos are specified at 2 ulp
+    bad = np.array([np.nan, np.inf, -np.inf])
+    sb, cb = np.zeros(3), np.zeros(3)
+    lib().hs_sincos_f64(bad.ctypes.data_as(vp), 3, sb.ctypes.data_as(vp), cb.ctypes.data_as(vp))
+    assert np.all(np.isnan(sb)) and np.all(np.isnan(cb))
+    xf = rng.uniform(-100, 100, 4000).astype(np.float32)
+    sf, cf = np.zeros_like(xf), np.zeros_like(xf)
+    lib().hs_sincos_f32(xf.ctypes.data_as(vp), len(xf), sf.ctypes.data_as(vp), cf.ctypes.data_as(vp))
+    assert np.max(np.abs(sf - np.sin(xf.astype(np.float64)))) <= 3e-7 and np.max(np.abs(cf - np.cos(xf.astype(np.float64)))) <= 3e-7

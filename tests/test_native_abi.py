@@ -1,0 +1,102 @@
+"""The C-ABI library: loads without a GPU, exports every symbol include/curiousrl_b200.h declares,
+validates its arguments before touching CUDA, and the Python layer fails loudly without a device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "curiousrl_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(crl_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from curiousrl_b200 import _native
+    lib = _native.load()
+    names = header_functions()
+    assert len(names) >= 13
+    for name in names:
+        assert hasattr(lib, name), "symbol %s declared in the header is not exported" % name
+    assert sorted(_native.EXPORTS) == names
+    assert lib.crl_abi_version() == 1
+
+
+def test_model_tables_and_status_strings():
+    from curiousrl_b200 import _native
+    assert _native.model_dims(0) == (6, 2, 2) and _native.model_dims(1) == (8, 3, 2) and _native.model_dims(2) == (6, 2, 2)
+    assert _native.model_default_bounds(1) == (-100.0, 100.0) and _native.model_default_bounds(2) == (-500.0, 500.0)
+    lib = _native.load()
+    assert lib.crl_model_dims(7, None, None, None) == -2
+    assert b"unsupported model" in lib.crl_status_string(-2)
+    assert lib.crl_status_string(0) == b"ok"
+    with pytest.raises(RuntimeError, match="unsupported model"):
+        _native.model_dims(99)
+
+
+def test_argument_validation_happens_before_any_cuda_call():
+    """Bad descriptors are rejected with status codes, not crashes - also on a box without a GPU."""
+    from curiousrl_b200 import _native
+    lib = _native.load()
+    good = dict(model=1, dtype=0, batch=4, horizon=10, params_stride_t=0, params_stride_b=2, params=0x1000,
+                u_lo=-100.0, u_hi=100.0)
+
+    def prob(**kw):
+        d = dict(good)
+        d.update(kw)
+        return _native.Problem(d["model"], d["dtype"], d["batch"], d["horizon"], d["params_stride_t"],
+                               d["params_stride_b"], d["params"], d["u_lo"], d["u_hi"])
+
+    opts = _native.SolverOpts(10, 1, 1e-6, 10, 0.5, 0, 0, 0, 0)
+    dummy = ctypes.c_void_p(0x1000)
+    assert lib.crl_rollout(None, dummy, None, 0, dummy, None, None) == -1
+    assert lib.crl_rollout(prob(model=5), dummy, None, 0, dummy, None, None) == -2
+    assert lib.crl_rollout(prob(dtype=3), dummy, None, 0, dummy, None, None) == -1
+    assert lib.crl_rollout(prob(horizon=0), dummy, None, 0, dummy, None, None) == -1
+    assert lib.crl_rollout(prob(batch=-1), dummy, None, 0, dummy, None, None) == -1
+    assert lib.crl_rollout(prob(params_stride_t=3), dummy, None, 0, dummy, None, None) == -1
+    assert lib.crl_rollout(prob(u_lo=1.0, u_hi=-1.0), dummy, None, 0, dummy, None, None) == -1
+    assert lib.crl_rollout(prob(batch=0), None, None, 0, None, None, None) == 0          # empty batch: nothing to do
+    assert lib.crl_rollout(prob(), None, None, 0, dummy, None, None) == -1               # missing x0
+    bad_opts = _native.SolverOpts(10, 1, 1e-6, 10, 0.5, 7, 0, 0, 0)
+    assert lib.crl_forward_pass(prob(), ctypes.byref(bad_opts), dummy, dummy, dummy, dummy, dummy, dummy, dummy, dummy,
+                                None) == -1
+    assert lib.crl_backward_dense(5, 2, 0, 1, 10, dummy, dummy, dummy, dummy, dummy, None) == -2
+    assert lib.crl_solve_workspace_bytes(ctypes.byref(prob(model=9)), ctypes.byref(opts)) == 0
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from curiousrl_b200 import logger
+    from curiousrl_b200.algorithm.ilqr_solver import BasiciLQR, DeviceModel
+    from conftest import make_scenario
+    logger.set_level(45)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        BasiciLQR(max_line_search=10).init(make_scenario("TwoLinkPlanarManipulator", 100))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        DeviceModel("ThreeLinkPlanarManipulator", 100, -100.0, 100.0)
+    # a host pointer (or no device at all) never reaches a kernel
+    from curiousrl_b200 import _native
+    lib = _native.load()
+    x = np.zeros(8)
+    prob = _native.Problem(1, 0, 1, 10, 0, 0, x.ctypes.data, -100.0, 100.0)
+    rc = lib.crl_rollout(prob, x.ctypes.data_as(ctypes.c_void_p), None, 0, x.ctypes.data_as(ctypes.c_void_p), None, None)
+    assert rc < 0
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under curiousrl_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "curiousrl_b200")
+    for base, _dirs, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(base, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "hostsim" not in text or f == "ilqr_common.cuh", f

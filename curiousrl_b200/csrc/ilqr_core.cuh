@@ -74,47 +74,48 @@ CRL_HD double rollout_open(const R* x0, int sx0, const R* U, int su_t, const Par
 }
 
 // -----------------------------------------------------------------------------------------
-// Closed-loop rollout  u = u_old + K (x_new - x_old) + alpha k  for one step size.
+// Where a closed-loop rollout gets its per-step inputs (old states/actions, K, k) from.
+// DirectFeed loads them from global memory through strided views (API layout, host build,
+// cooperative straggler mode).  The solve kernel's TileFeed (ilqr_kernels.cu) streams whole
+// time-step blocks of the warp tile into shared memory one step ahead with bulk async copies.
 // KN = number of state columns stored per row of K (N for the API layout; NS in the solver's
 // workspace, where the output columns are structurally zero and not stored).
-template <class Mdl, class R, int KN, int SCX, int SCK, int SCXN>
-CRL_HD double rollout_closed(View<R, Mdl::D, SCX> Xold, View<R, Mdl::M * KN, SCK> Kv, View<R, Mdl::M, SCK> kv,
-                             R alpha, const ParamRef<R>& prm, const Bounds<R>& ub, int T,
-                             View<R, Mdl::D, SCXN> Xnew) {
-    constexpr int N = Mdl::N, M = Mdl::M, D = Mdl::D;
-    R xu[D], xn[N];
-    {
+template <class Mdl, class R, int KN, int SCX, int SCK>
+struct DirectFeed {
+    static constexpr int kKN = KN;
+    View<R, Mdl::D, SCX> Xold;
+    View<R, Mdl::M * KN, SCK> Kv;
+    View<R, Mdl::M, SCK> kv;
+    CRL_HD void begin(int) {}
+    CRL_HD void end() {}
+    CRL_HD void row0(R* xu) const {
         const R* row = Xold.row(0);
-        CRL_UNROLL for (int i = 0; i < D; ++i) xu[i] = Xold.ld(row, i);   // row 0 copied whole (:121)
+        CRL_UNROLL for (int i = 0; i < Mdl::D; ++i) xu[i] = Xold.ld(row, i);
     }
-    // software pipeline: the inputs of step t+1 (old states/actions, K, k) are fetched into
-    // registers while step t computes, so one warp keeps its loads in flight across its own math
-    R xo_n[KN], uo_n[M], K_n[M * KN], k_n[M];
-    if (T > 1) {
-        const R* xo = Xold.row(0);
-        const R* Kr = Kv.row(0);
-        const R* kr = kv.row(0);
-        CRL_UNROLL for (int j = 0; j < KN; ++j) xo_n[j] = Xold.ld(xo, j);
-        CRL_UNROLL for (int a = 0; a < M; ++a) uo_n[a] = Xold.ld(xo, N + a);
-        CRL_UNROLL for (int j = 0; j < M * KN; ++j) K_n[j] = Kv.ld(Kr, j);
-        CRL_UNROLL for (int a = 0; a < M; ++a) k_n[a] = kv.ld(kr, a);
+    CRL_HD void get(int t, R* xo, R* uo, R* Kc, R* kc) const {
+        const R* xr = Xold.row(t);
+        const R* Kr = Kv.row(t);
+        const R* kr = kv.row(t);
+        CRL_UNROLL for (int j = 0; j < KN; ++j) xo[j] = Xold.ld(xr, j);
+        CRL_UNROLL for (int a = 0; a < Mdl::M; ++a) uo[a] = Xold.ld(xr, Mdl::N + a);
+        CRL_UNROLL for (int j = 0; j < Mdl::M * KN; ++j) Kc[j] = Kv.ld(Kr, j);
+        CRL_UNROLL for (int a = 0; a < Mdl::M; ++a) kc[a] = kv.ld(kr, a);
     }
+};
+
+// Closed-loop rollout  u = u_old + K (x_new - x_old) + alpha k  for one step size
+// (ilqr_dynamic_model.py:111-134) with the cost of the new trajectory (ilqr_obj_fun.py:86-95).
+template <class Mdl, class R, class Feed, int SCXN>
+CRL_HD double rollout_closed_f(Feed& feed, R alpha, const ParamRef<R>& prm, const Bounds<R>& ub, int T,
+                               View<R, Mdl::D, SCXN> Xnew) {
+    constexpr int N = Mdl::N, M = Mdl::M, D = Mdl::D, KN = Feed::kKN;
+    R xu[D], xn[N];
+    feed.begin(T - 1);
+    feed.row0(xu);                                                        // row 0 copied whole (:121)
     double J = 0.0;
     for (int t = 0; t < T - 1; ++t) {
         R xo_c[KN], uo_c[M], K_c[M * KN], k_c[M];
-        CRL_UNROLL for (int j = 0; j < KN; ++j) xo_c[j] = xo_n[j];
-        CRL_UNROLL for (int a = 0; a < M; ++a) uo_c[a] = uo_n[a];
-        CRL_UNROLL for (int j = 0; j < M * KN; ++j) K_c[j] = K_n[j];
-        CRL_UNROLL for (int a = 0; a < M; ++a) k_c[a] = k_n[a];
-        if (t + 1 < T - 1) {
-            const R* xo = Xold.row(t + 1);
-            const R* Kr = Kv.row(t + 1);
-            const R* kr = kv.row(t + 1);
-            CRL_UNROLL for (int j = 0; j < KN; ++j) xo_n[j] = Xold.ld(xo, j);
-            CRL_UNROLL for (int a = 0; a < M; ++a) uo_n[a] = Xold.ld(xo, N + a);
-            CRL_UNROLL for (int j = 0; j < M * KN; ++j) K_n[j] = Kv.ld(Kr, j);
-            CRL_UNROLL for (int a = 0; a < M; ++a) k_n[a] = kv.ld(kr, a);
-        }
+        feed.get(t, xo_c, uo_c, K_c, k_c);
         R dx[KN];
         CRL_UNROLL for (int j = 0; j < KN; ++j) dx[j] = xu[j] - xo_c[j];
         CRL_UNROLL for (int a = 0; a < M; ++a) {
@@ -131,6 +132,7 @@ CRL_HD double rollout_closed(View<R, Mdl::D, SCX> Xold, View<R, Mdl::M * KN, SCK
         model_step<Mdl, R>(xu, xn);
         CRL_UNROLL for (int i = 0; i < N; ++i) xu[i] = xn[i];
     }
+    feed.end();
     if (T > 1) {
         CRL_UNROLL for (int a = 0; a < M; ++a) xu[N + a] = R(0);         // last action stays 0 (:133)
     }
@@ -140,6 +142,14 @@ CRL_HD double rollout_closed(View<R, Mdl::D, SCX> Xold, View<R, Mdl::M * KN, SCK
     return J;
 }
 
+template <class Mdl, class R, int KN, int SCX, int SCK, int SCXN>
+CRL_HD double rollout_closed(View<R, Mdl::D, SCX> Xold, View<R, Mdl::M * KN, SCK> Kv, View<R, Mdl::M, SCK> kv,
+                             R alpha, const ParamRef<R>& prm, const Bounds<R>& ub, int T,
+                             View<R, Mdl::D, SCXN> Xnew) {
+    DirectFeed<Mdl, R, KN, SCX, SCK> feed{Xold, Kv, kv};
+    return rollout_closed_f<Mdl, R>(feed, alpha, prm, ub, T, Xnew);
+}
+
 // -----------------------------------------------------------------------------------------
 // NA step sizes in ONE pass over the stored data: the old trajectory, K and k are read once
 // and shared by all candidates (this is what makes the line search move its algorithmic bytes
@@ -147,29 +157,23 @@ CRL_HD double rollout_closed(View<R, Mdl::D, SCX> Xold, View<R, Mdl::M * KN, SCK
 // Per candidate the arithmetic is exactly rollout_closed's, so every J[a] is bit-identical to
 // a separate single-alpha call.  Only the candidate with index `keep` (per lane) is written
 // to Xnew (STORE = false: none); a different winner is re-materialised by one rollout_closed call.
-template <class Mdl, class R, int NA, int KN, int SCX, int SCK, int SCXN, bool STORE = true>
-CRL_HD void rollout_multi(View<R, Mdl::D, SCX> Xold, View<R, Mdl::M * KN, SCK> Kv, View<R, Mdl::M, SCK> kv,
-                          const R (&alpha)[NA], const ParamRef<R>& prm, const Bounds<R>& ub, int T, int keep,
-                          View<R, Mdl::D, SCXN> Xnew, double (&J)[NA]) {
-    constexpr int N = Mdl::N, M = Mdl::M, D = Mdl::D;
+template <class Mdl, class R, int NA, class Feed, int SCXN, bool STORE = true>
+CRL_HD void rollout_multi_f(Feed& feed, const R (&alpha)[NA], const ParamRef<R>& prm, const Bounds<R>& ub, int T,
+                            int keep, View<R, Mdl::D, SCXN> Xnew, double (&J)[NA]) {
+    constexpr int N = Mdl::N, M = Mdl::M, D = Mdl::D, KN = Feed::kKN;
     R xu[NA][D];
+    feed.begin(T - 1);
     {
-        const R* row = Xold.row(0);
+        R x0[D];
+        feed.row0(x0);
         CRL_UNROLL for (int i = 0; i < D; ++i) {
-            const R v = Xold.ld(row, i);
-            CRL_UNROLL for (int a = 0; a < NA; ++a) xu[a][i] = v;
+            CRL_UNROLL for (int a = 0; a < NA; ++a) xu[a][i] = x0[i];
         }
     }
     CRL_UNROLL for (int a = 0; a < NA; ++a) J[a] = 0.0;
     for (int t = 0; t < T - 1; ++t) {
-        const R* xo = Xold.row(t);
-        const R* Kr = Kv.row(t);
-        const R* kr = kv.row(t);
         R xo_c[KN], uo_c[M], K_c[M * KN], k_c[M];
-        CRL_UNROLL for (int j = 0; j < KN; ++j) xo_c[j] = Xold.ld(xo, j);
-        CRL_UNROLL for (int a = 0; a < M; ++a) uo_c[a] = Xold.ld(xo, N + a);
-        CRL_UNROLL for (int j = 0; j < M * KN; ++j) K_c[j] = Kv.ld(Kr, j);
-        CRL_UNROLL for (int a = 0; a < M; ++a) k_c[a] = kv.ld(kr, a);
+        feed.get(t, xo_c, uo_c, K_c, k_c);
         CRL_UNROLL for (int c = 0; c < NA; ++c) {
             R dx[KN];
             CRL_UNROLL for (int j = 0; j < KN; ++j) dx[j] = xu[c][j] - xo_c[j];
@@ -203,6 +207,7 @@ CRL_HD void rollout_multi(View<R, Mdl::D, SCX> Xold, View<R, Mdl::M * KN, SCK> K
             }
         }
     }
+    feed.end();
     CRL_UNROLL for (int c = 0; c < NA; ++c) {
         if (T > 1) {
             CRL_UNROLL for (int a = 0; a < M; ++a) xu[c][N + a] = R(0);
@@ -217,6 +222,14 @@ CRL_HD void rollout_multi(View<R, Mdl::D, SCX> Xold, View<R, Mdl::M * KN, SCK> K
             Xnew.st(row, i, v);
         }
     }
+}
+
+template <class Mdl, class R, int NA, int KN, int SCX, int SCK, int SCXN, bool STORE = true>
+CRL_HD void rollout_multi(View<R, Mdl::D, SCX> Xold, View<R, Mdl::M * KN, SCK> Kv, View<R, Mdl::M, SCK> kv,
+                          const R (&alpha)[NA], const ParamRef<R>& prm, const Bounds<R>& ub, int T, int keep,
+                          View<R, Mdl::D, SCXN> Xnew, double (&J)[NA]) {
+    DirectFeed<Mdl, R, KN, SCX, SCK> feed{Xold, Kv, kv};
+    rollout_multi_f<Mdl, R, NA, DirectFeed<Mdl, R, KN, SCX, SCK>, SCXN, STORE>(feed, alpha, prm, ub, T, keep, Xnew, J);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -418,16 +431,28 @@ CRL_HD void riccati_step(const R* xu, const R* p, ValueFn<Mdl, R>& vf, R (&Kout)
 // Backward pass over a stored trajectory; F, c, C are recomputed per step.
 // K is written with KN state columns per row (KN = N: output columns get -0.0, as the
 // reference's -solve(Quu, 0) does; KN = NS: compact workspace form).
-template <class Mdl, class R, int KN, int SCX, int SCK>
-CRL_HD void backward_fused(View<R, Mdl::D, SCX> X, const ParamRef<R>& prm, int T,
-                           View<R, Mdl::M * KN, SCK> Kv, View<R, Mdl::M, SCK> kv) {
+template <class Mdl, class R, int SCX>
+struct DirectRowFeed {                       // rows of a stored trajectory, last to first
+    View<R, Mdl::D, SCX> X;
+    int T;
+    CRL_HD void begin(int) {}
+    CRL_HD void end() {}
+    CRL_HD void get(int i, R* xu) const {    // i-th row handed out = time step T-1-i
+        const R* row = X.row(T - 1 - i);
+        CRL_UNROLL for (int c = 0; c < Mdl::D; ++c) xu[c] = X.ld(row, c);
+    }
+};
+
+template <class Mdl, class R, int KN, class RowFeed, int SCK>
+CRL_HD void backward_fused_f(RowFeed& rows, const ParamRef<R>& prm, int T, View<R, Mdl::M * KN, SCK> Kv,
+                             View<R, Mdl::M, SCK> kv) {
     constexpr int NS = Mdl::NS, M = Mdl::M, D = Mdl::D, P = Mdl::P;
     ValueFn<Mdl, R> vf;
     vf.clear();
+    rows.begin(T);
     for (int t = T - 1; t >= 0; --t) {
         R xu[D], p[P], Kt[M][NS], kt[M];
-        const R* row = X.row(t);
-        CRL_UNROLL for (int i = 0; i < D; ++i) xu[i] = X.ld(row, i);
+        rows.get(T - 1 - t, xu);
         CRL_UNROLL for (int i = 0; i < P; ++i) p[i] = prm.get(t, i);
         riccati_step<Mdl, R>(xu, p, vf, Kt, kt);
         R* Kr = Kv.row(t);
@@ -437,6 +462,14 @@ CRL_HD void backward_fused(View<R, Mdl::D, SCX> X, const ParamRef<R>& prm, int T
             kv.st(kr, a, kt[a]);
         }
     }
+    rows.end();
+}
+
+template <class Mdl, class R, int KN, int SCX, int SCK>
+CRL_HD void backward_fused(View<R, Mdl::D, SCX> X, const ParamRef<R>& prm, int T,
+                           View<R, Mdl::M * KN, SCK> Kv, View<R, Mdl::M, SCK> kv) {
+    DirectRowFeed<Mdl, R, SCX> rows{X, T};
+    backward_fused_f<Mdl, R, KN>(rows, prm, T, Kv, kv);
 }
 
 // Materialised derivatives of one row (API / stage parity): F [N][D], c [D], C [D][D] row-major.

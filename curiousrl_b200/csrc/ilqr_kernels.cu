@@ -157,6 +157,154 @@ __global__ void __launch_bounds__(kBlock) forward_pass_kernel(ProblemDev<R> pb, 
     stop[b] = stop_test(Jn, Jl, op.criterion, op.stop_method == CRL_STOP_RELATIVE) ? 1 : 0;
 }
 
+// ------------------------------------------------------------------------------ smem staging (TMA)
+// Bulk asynchronous copies (cp.async.bulk, the 1-D TMA path; SASS UBLKCP) stream the next time
+// step's contiguous tile blocks into shared memory while the current step computes; completion is
+// tracked by an mbarrier per stage.  One elected lane issues the copies, every lane of the warp
+// that takes part waits on the barrier and then reads its own column (conflict-free LDS).
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_reinit(unsigned long long* bar) {
+    const unsigned a = smem_addr(bar);
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(a) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned a = smem_addr(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+// Per-warp staging area: two stages of one time step's X / K / k blocks + two mbarriers.
+template <class Mdl, class R>
+struct StageLayout {
+    static constexpr int XB = Mdl::D * 32, KB = Mdl::M * Mdl::NS * 32, kB = Mdl::M * 32;   // reals per block
+    static constexpr int STAGE = XB + KB + kB;
+    static constexpr int kWarpBytes = 2 * STAGE * (int)sizeof(R) + 128;                     // + barriers (padded)
+};
+
+// Closed-loop rollout inputs of the warp's own tiles (KN = NS).
+template <class Mdl, class R>
+struct TileFeed {
+    using L = StageLayout<Mdl, R>;
+    static constexpr int kKN = Mdl::NS;
+    const R* gX;                  // column 0, t = 0 of the old trajectory tile
+    const R* gK;
+    const R* gk;
+    R* sm;                        // this warp's two stages
+    unsigned long long* bar;      // this warp's two barriers
+    unsigned mask;
+    int lane, leader, nsteps;
+
+    // `mask_` = the lanes that take part, computed by the caller where the warp is still converged
+    __device__ TileFeed(unsigned mask_, const R* gX_, const R* gK_, const R* gk_, R* sm_, unsigned long long* bar_)
+        : gX(gX_), gK(gK_), gk(gk_), sm(sm_), bar(bar_) {
+        mask = mask_;
+        lane = threadIdx.x & 31;
+        leader = __ffs(mask) - 1;
+        nsteps = 0;
+    }
+    __device__ void issue(int t) {
+        const int st = t & 1;
+        R* dst = sm + st * L::STAGE;
+        mbar_expect_tx(bar + st, (unsigned)(L::STAGE * sizeof(R)));
+        bulk_g2s(dst, gX + (size_t)t * L::XB, L::XB * sizeof(R), bar + st);
+        bulk_g2s(dst + L::XB, gK + (size_t)t * L::KB, L::KB * sizeof(R), bar + st);
+        bulk_g2s(dst + L::XB + L::KB, gk + (size_t)t * L::kB, L::kB * sizeof(R), bar + st);
+    }
+    __device__ void begin(int n) {
+        nsteps = n;
+        __syncwarp(mask);
+        if (lane == leader) {
+            mbar_reinit(bar);
+            mbar_reinit(bar + 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            if (n > 0) issue(0);
+        }
+        __syncwarp(mask);
+    }
+    __device__ void end() { __syncwarp(mask); }
+    __device__ void row0(R* xu) const {
+#pragma unroll
+        for (int i = 0; i < Mdl::D; ++i) xu[i] = gX[i * 32 + lane];
+    }
+    __device__ void get(int t, R* xo, R* uo, R* Kc, R* kc) {
+        __syncwarp(mask);                                   // everyone is done with the stage about to be refilled
+        if (lane == leader && t + 1 < nsteps) issue(t + 1);
+        mbar_wait(bar + (t & 1), (unsigned)((t >> 1) & 1));
+        const R* s0 = sm + (t & 1) * L::STAGE + lane;
+#pragma unroll
+        for (int j = 0; j < Mdl::NS; ++j) xo[j] = s0[j * 32];
+#pragma unroll
+        for (int a = 0; a < Mdl::M; ++a) uo[a] = s0[(Mdl::N + a) * 32];
+#pragma unroll
+        for (int j = 0; j < Mdl::M * Mdl::NS; ++j) Kc[j] = s0[L::XB + j * 32];
+#pragma unroll
+        for (int a = 0; a < Mdl::M; ++a) kc[a] = s0[L::XB + L::KB + a * 32];
+    }
+};
+
+// Rows of the current trajectory tile, last to first, for the backward pass.
+template <class Mdl, class R>
+struct TileRowFeed {
+    using L = StageLayout<Mdl, R>;
+    const R* gX;
+    R* sm;
+    unsigned long long* bar;
+    unsigned mask;
+    int lane, leader, nrows;
+    __device__ TileRowFeed(unsigned mask_, const R* gX_, R* sm_, unsigned long long* bar_)
+        : gX(gX_), sm(sm_), bar(bar_) {
+        mask = mask_;
+        lane = threadIdx.x & 31;
+        leader = __ffs(mask) - 1;
+        nrows = 0;
+    }
+    __device__ void issue(int i) {
+        const int st = i & 1;
+        mbar_expect_tx(bar + st, (unsigned)(L::XB * sizeof(R)));
+        bulk_g2s(sm + st * L::STAGE, gX + (size_t)(nrows - 1 - i) * L::XB, L::XB * sizeof(R), bar + st);
+    }
+    __device__ void begin(int n) {
+        nrows = n;
+        __syncwarp(mask);
+        if (lane == leader) {
+            mbar_reinit(bar);
+            mbar_reinit(bar + 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            if (n > 0) issue(0);
+        }
+        __syncwarp(mask);
+    }
+    __device__ void end() { __syncwarp(mask); }
+    __device__ void get(int i, R* xu) {
+        __syncwarp(mask);
+        if (lane == leader && i + 1 < nrows) issue(i + 1);
+        mbar_wait(bar + (i & 1), (unsigned)((i >> 1) & 1));
+        const R* s0 = sm + (i & 1) * L::STAGE + lane;
+#pragma unroll
+        for (int c = 0; c < Mdl::D; ++c) xu[c] = s0[c * 32];
+    }
+};
+
 // ------------------------------------------------------------------------------ persistent solve
 template <class R>
 struct SolveArgs {
@@ -192,6 +340,19 @@ __global__ void __launch_bounds__(kBlock, MINB) solve_kernel(SolveArgs<R> a) {
     const View<R, D, 32> Xbuf0{wsb}, Xbuf1{wsb + (size_t)T * D * 32};
     const View<R, M * NS, 32> Kv{wsb + (size_t)2 * T * D * 32};
     const View<R, M, 32> kv{wsb + (size_t)2 * T * D * 32 + (size_t)T * M * NS * 32};
+
+    // per-warp staging area in dynamic shared memory
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using SL = StageLayout<Mdl, R>;
+    unsigned char* const my_sm = smem_raw + (threadIdx.x >> 5) * SL::kWarpBytes;
+    R* const stage_sm = reinterpret_cast<R*>(my_sm);
+    unsigned long long* const stage_bar = reinterpret_cast<unsigned long long*>(my_sm + 2 * SL::STAGE * sizeof(R));
+    if (lane == 0) {
+        mbar_init(stage_bar);
+        mbar_init(stage_bar + 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
 
     int cur = 0;                 // warp-uniform: which X buffer holds the current trajectories
     bool exhausted = false;      // warp-uniform: the global queue is empty
@@ -230,7 +391,11 @@ __global__ void __launch_bounds__(kBlock, MINB) solve_kernel(SolveArgs<R> a) {
         const View<R, D, 32> Xn = cur ? Xbuf0 : Xbuf1;
 
         // ---- backward pass: K, k for every active lane
-        if (active) backward_fused<Mdl, R, NS, 32, 32>(Xc, prm, T, Kv, kv);
+        const unsigned act_mask = __ballot_sync(kFull, active);
+        if (active) {
+            TileRowFeed<Mdl, R> rows(act_mask, Xc.base - lane, stage_sm, stage_bar);
+            backward_fused_f<Mdl, R, NS>(rows, prm, T, Kv, kv);
+        }
 
         // ---- line search: first improving alpha = 1, g, g^2, ...
         bool accepted = false;
@@ -300,7 +465,8 @@ __global__ void __launch_bounds__(kBlock, MINB) solve_kernel(SolveArgs<R> a) {
             int a0 = 0;
             while (a0 < tries) {
                 const bool pending = active && !accepted;
-                if (!__any_sync(kFull, pending)) break;
+                const unsigned pend_mask = __ballot_sync(kFull, pending);
+                if (pend_mask == 0u) break;
                 // a warp whose pending lanes all expect alpha = 1 to be accepted tries it alone first
                 const bool wide = (tries - a0 >= 2) && (a0 > 0 || __any_sync(kFull, pending && pred > 0));
                 if (wide) {
@@ -316,7 +482,8 @@ __global__ void __launch_bounds__(kBlock, MINB) solve_kernel(SolveArgs<R> a) {
                         int keep = pred - a0;
                         keep = keep < 0 ? 0 : (keep > kLsChunk - 1 ? kLsChunk - 1 : keep);
                         double Jc[kLsChunk];
-                        rollout_multi<Mdl, R, kLsChunk, NS, 32, 32, 32>(Xc, Kv, kv, al, prm, a.pb.ub, T, keep, Xn, Jc);
+                        TileFeed<Mdl, R> feed(pend_mask, Xc.base - lane, Kv.base - lane, kv.base - lane, stage_sm, stage_bar);
+                        rollout_multi_f<Mdl, R, kLsChunk, TileFeed<Mdl, R>, 32, true>(feed, al, prm, a.pb.ub, T, keep, Xn, Jc);
     #pragma unroll
                         for (int c = 0; c < kLsChunk; ++c) {
                             if (!accepted && a0 + c < tries && ls_accept(Jc[c], J_last, feas)) {
@@ -331,7 +498,8 @@ __global__ void __launch_bounds__(kBlock, MINB) solve_kernel(SolveArgs<R> a) {
                     a0 += kLsChunk;
                 } else {
                     if (pending) {
-                        const double Jt = rollout_closed<Mdl, R, NS, 32, 32, 32>(Xc, Kv, kv, (R)alpha, prm, a.pb.ub, T, Xn);
+                        TileFeed<Mdl, R> feed(pend_mask, Xc.base - lane, Kv.base - lane, kv.base - lane, stage_sm, stage_bar);
+                        const double Jt = rollout_closed_f<Mdl, R>(feed, (R)alpha, prm, a.pb.ub, T, Xn);
                         if (a.op.ls_method == CRL_LS_NONE || ls_accept(Jt, J_last, feas)) {
                             accepted = true;
                             J_new = Jt;
@@ -342,8 +510,12 @@ __global__ void __launch_bounds__(kBlock, MINB) solve_kernel(SolveArgs<R> a) {
                     a0 += 1;
                 }
             }
-            if (__any_sync(kFull, replay)) {
-                if (replay) rollout_closed<Mdl, R, NS, 32, 32, 32>(Xc, Kv, kv, (R)alpha_taken, prm, a.pb.ub, T, Xn);
+            const unsigned replay_mask = __ballot_sync(kFull, replay);
+            if (replay_mask != 0u) {
+                if (replay) {
+                    TileFeed<Mdl, R> feed(replay_mask, Xc.base - lane, Kv.base - lane, kv.base - lane, stage_sm, stage_bar);
+                    rollout_closed_f<Mdl, R>(feed, (R)alpha_taken, prm, a.pb.ub, T, Xn);
+                }
             }
         }
         if (accepted) pred = taken;
@@ -501,7 +673,10 @@ static int solve_grid_v(int requested) {
     int dev = 0, sms = 0, per_sm = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel<Mdl, R, MINB>, kBlock, 0) != cudaSuccess)
+    constexpr int smem = (kBlock / 32) * StageLayout<Mdl, R>::kWarpBytes;
+    if (cudaFuncSetAttribute(solve_kernel<Mdl, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+        return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel<Mdl, R, MINB>, kBlock, smem) != cudaSuccess)
         return -1;
     if (per_sm < 1) per_sm = 1;
     return sms * per_sm;
@@ -522,10 +697,11 @@ static int solve_grid(int requested, int variant) {
 template <class Mdl, class R>
 static void solve_launch(int variant, int grid, cudaStream_t s, const SolveArgs<R>& a) {
     const int v = variant > 0 ? variant : SolveCfg<R>::MINB;
+    constexpr int smem = (kBlock / 32) * StageLayout<Mdl, R>::kWarpBytes;
     switch (v) {
-        case 2: solve_kernel<Mdl, R, 2><<<grid, kBlock, 0, s>>>(a); break;
-        case 3: solve_kernel<Mdl, R, 3><<<grid, kBlock, 0, s>>>(a); break;
-        default: solve_kernel<Mdl, R, 4><<<grid, kBlock, 0, s>>>(a); break;
+        case 2: solve_kernel<Mdl, R, 2><<<grid, kBlock, smem, s>>>(a); break;
+        case 3: solve_kernel<Mdl, R, 3><<<grid, kBlock, smem, s>>>(a); break;
+        default: solve_kernel<Mdl, R, 4><<<grid, kBlock, smem, s>>>(a); break;
     }
 }
 

@@ -65,6 +65,12 @@ def load():
     """Load (building first if the in-tree library is missing or stale and nvcc is present)."""
     global _lib
     if _lib is None:
+        path = os.environ.get("CURIOUSRL_B200_LIB")          # tuning experiments: load an alternative build
+        if path:
+            lib = ctypes.CDLL(path)
+            _declare(lib)
+            _lib = lib
+            return _lib
         path = _build.LIB_PATH
         if _build.is_stale() and _build.find_nvcc() is not None:
             path = _build.build_native()

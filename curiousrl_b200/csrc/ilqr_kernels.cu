@@ -681,7 +681,7 @@ static unsigned blocks_for(long long work) { return (unsigned)((work + kBlock - 
 //   11      : 8 warps per CTA, 1 CTA per SM, warps phase-locked (SYNC)
 //   12      : 4 warps per CTA, 2 CTAs per SM, phase-locked
 template <class R> struct SolveCfg;
-template <> struct SolveCfg<double> { static constexpr int kDefault = 11; };
+template <> struct SolveCfg<double> { static constexpr int kDefault = 12; };
 template <> struct SolveCfg<float> { static constexpr int kDefault = 4; };
 
 template <class Mdl, class R, int WARPS, int MINB, bool SYNC>

@@ -11,6 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int
 
 from . import build as _build
 
+ABI_VERSION = 2
 MODEL_IDS = {"TwoLinkPlanarManipulator": 0, "ThreeLinkPlanarManipulator": 1, "RoboticArmTracking": 2}
 DTYPE_IDS = {"float64": 0, "float32": 1}
 LINE_SEARCH_IDS = {"vanilla": 0, "feasibility": 1, "none": 2}
@@ -31,7 +32,8 @@ class Problem(Structure):
 class SolverOpts(Structure):
     _fields_ = [("max_iter", c_int32), ("is_check_stop", c_int32), ("stopping_criterion", c_double),
                 ("max_line_search", c_int32), ("gamma", c_double), ("line_search_method", c_int32),
-                ("stopping_method", c_int32), ("grid_blocks", c_int32), ("reserved", c_int32)]
+                ("stopping_method", c_int32), ("grid_blocks", c_int32), ("reserved", c_int32),
+                ("coop_threshold", c_int32), ("reserved2", c_int32)]
 
 
 _lib = None
@@ -79,7 +81,7 @@ def load():
                                "There is no CPU fallback for the iLQR path." % path)
         lib = ctypes.CDLL(path)
         _declare(lib)
-        if lib.crl_abi_version() != 1:
+        if lib.crl_abi_version() != ABI_VERSION:
             raise RuntimeError("curiousrl_b200: ABI version mismatch in %s" % path)
         _lib = lib
     return _lib

@@ -136,7 +136,7 @@ class iLQRWrapper(AlgoWrapper):
                                   int(self._max_line_search), float(self._gamma),
                                   _native.LINE_SEARCH_IDS[self._line_search_method],
                                   _native.STOPPING_IDS[self._stopping_method], int(getattr(self, "_grid_blocks", 0)),
-                                  int(getattr(self, "_occupancy", 0)))
+                                  int(getattr(self, "_occupancy", 0)), int(getattr(self, "_coop_threshold", 0)), 0)
 
     def _params_for(self, B: int) -> torch.Tensor:
         """The solver's current add_param ([T, p], reference semantics) as a device tensor shared by B problems."""
@@ -188,12 +188,14 @@ class BasiciLQR(iLQRWrapper):
     Extra, defaulted constructor arguments: `dtype` ("float64" | "float32": arithmetic of the
     rollouts and the Riccati pass; costs are always accumulated in float64), `device` (torch
     device, default: current CUDA device), `verify` (check the scenario's symbolic definition
-    against the device model at init), `grid_blocks` (persistent-kernel grid, 0 = auto).
+    against the device model at init), `grid_blocks` (persistent-kernel grid, 0 = auto),
+    `coop_threshold` (scheduling of the tail of a batched solve, see include/curiousrl_b200.h;
+    results do not depend on it).
     """
 
     def __init__(self, max_iter=1000, is_check_stop=True, stopping_criterion=1e-6, max_line_search=50, gamma=0.5,
                  line_search_method="vanilla", stopping_method="relative", dtype="float64", device=None, verify=True,
-                 grid_blocks=0, occupancy=0):
+                 grid_blocks=0, occupancy=0, coop_threshold=0):
         super().__init__(stopping_criterion=stopping_criterion, max_line_search=max_line_search, gamma=gamma,
                          line_search_method=line_search_method, stopping_method=stopping_method,
                          max_iter=max_iter, is_check_stop=is_check_stop)
@@ -204,6 +206,7 @@ class BasiciLQR(iLQRWrapper):
         self._verify = verify
         self._grid_blocks = grid_blocks
         self._occupancy = occupancy      # resident CTAs/SM variant of the solve kernel (0 = default)
+        self._coop_threshold = coop_threshold
         self._trajectory = None
         self.last_result: Optional[BatchResult] = None
 

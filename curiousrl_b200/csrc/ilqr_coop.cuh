@@ -1,0 +1,331 @@
+// Warp-cooperative iLQR iteration: one WARP = one trajectory (device only).
+//
+// The solve kernel's main mode maps one lane to one trajectory: best throughput, but one
+// iteration is a ~10^5-instruction dependent chain per lane, so a single slow trajectory
+// (the iteration counts are heavy tailed: median 13, p99 ~520, cap 1000) holds a whole warp
+// for ~1 ms per iteration.  Once the work queue is empty, warps therefore hand their remaining
+// trajectories to a global straggler queue and every warp of the grid becomes a "finisher":
+// it takes one straggler at a time and iterates it with all 32 lanes,
+//   * backward pass (ilqr_wrapper.py:232-256): every matrix element of the Riccati step is owned
+//     by one lane, operands are exchanged through shared memory (4 warp barriers per time step),
+//     the 3x3 / 2x2 pivoted LU of Quu is factored redundantly by every lane while the Q blocks are
+//     formed and applied to one right-hand-side column per lane;
+//   * line search (ilqr_wrapper.py:74-100): one step size per lane, all candidates at once.
+// Per element the arithmetic is the SAME operation sequence as the lane-per-trajectory code in
+// ilqr_core.cuh (riccati_step / rollout_closed_f), so a trajectory's result does not depend on
+// which path finished it (tests/test_gpu_solve_parity.py::test_coop_matches_lane_mode checks
+// bit equality).
+//
+// Implemented for the kinematic chains (TwoLink, ThreeLink: constant A, B; variable G only).
+#pragma once
+
+#include "ilqr_core.cuh"
+
+namespace crl {
+
+template <class Mdl> struct CoopSupport { static constexpr bool value = false; };
+template <> struct CoopSupport<TwoLink> { static constexpr bool value = true; };
+template <> struct CoopSupport<ThreeLink> { static constexpr bool value = true; };
+
+// Shared-memory layout (in reals) of one warp's cooperative backward pass.
+template <class Mdl>
+struct CoopLayout {
+    static constexpr int NS = Mdl::NS, M = Mdl::M, J = Mdl::M, NQ = Mdl::NS + 1;
+    static constexpr int V = 0;                       // NS x NS value-function Hessian, both triangles
+    static constexpr int VS = V + NS * NS;            // NS      value-function gradient
+    static constexpr int VY = VS + NS;                // 2       gradient w.r.t. the output entries
+    static constexpr int VYY = VY + 2;                // 2       (diagonal) Hessian w.r.t. the output entries
+    static constexpr int ZEND = VYY + 2;              // [0, ZEND) is zeroed at the start of a pass
+    static constexpr int ONE = ZEND;                  // the constant 1.0
+    static constexpr int GCUR = ONE + 1;              // 2 x J   variable Jacobian entries G[y][2i] of the current step
+    static constexpr int MA = GCUR + 2 * J;           // NS x NS A^T V
+    static constexpr int MB = MA + NS * NS;           // M x NS  B^T V
+    static constexpr int QX = MB + M * NS;            // NS x NQ [Qss (upper triangle) | qs]
+    static constexpr int QU = QX + NS * NQ;           // M x NQ  [Qus | qu]
+    static constexpr int KK = QU + M * NQ;            // M x NQ  [K | k]
+    static constexpr int GT = (KK + M * NQ + 1) & ~1; // [T][2J] G entries of every time step
+    __host__ __device__ static constexpr int reals(int T) { return GT + T * 2 * J; }
+};
+
+// i <= j < n enumerated row by row: element e of the upper triangle of an n-column matrix
+__device__ __forceinline__ void coop_pair(int e, int n, int& i, int& j) {
+    i = 0;
+    int len = n;
+    while (e >= len) {
+        e -= len;
+        ++i;
+        --len;
+    }
+    j = i + e;
+}
+
+enum CoopKind : int { CK_PLAIN = 0, CK_HPLUS = 1, CK_HONLY = 2 };
+
+// out = S[o1]            (PLAIN)
+//     = S[o0]*h + S[o1]  (HPLUS)
+//     = S[o1]*h          (HONLY; o0 == o1)
+template <class R>
+__device__ __forceinline__ R coop_hsum(const R* S, int o0, int o1, int kind, R h) {
+    const R m1 = S[o1];
+    const R p = S[o0] * h;
+    return kind == CK_PLAIN ? m1 : (kind == CK_HPLUS ? p + m1 : p);
+}
+
+// Backward pass of one trajectory (row-major Xc [T][D]) by the whole warp; writes K [T][M*NS]
+// and k [T][M] (row-major, global).  S = this warp's shared-memory area (CoopLayout).
+template <class Mdl, class R>
+__device__ void coop_backward(const R* Xc, const ParamRef<R>& prm, int T, R* Kb, R* kb, R* S, int lane) {
+    using L = CoopLayout<Mdl>;
+    constexpr int NS = Mdl::NS, M = Mdl::M, J = Mdl::M, N = Mdl::N, D = Mdl::D, NQ = NS + 1;
+    constexpr int N1 = NS * NS + M * NS, R1 = (N1 + 31) / 32;                     // stage 1: MA, MB
+    constexpr int NP = NS * (NS + 1) / 2;                                          // upper-triangle pairs
+    constexpr int N2 = NP + M * NS + NS + M, R2 = (N2 + 31) / 32;                 // stage 2: Qss, Qus, qs, qu
+    constexpr int N5 = NP + NS;                                                    // stage 5: V, v
+    static_assert(N5 + 2 <= 32 && NQ + 2 * J <= 32 && M * NQ <= 32, "element-to-lane mapping needs <= 32 lanes per stage");
+    const R h = R(kH);
+
+    // ---- G table: lanes take time steps lane, lane + 32, ...
+    for (int t = lane; t < T; t += 32) {
+        R xu[D], ang[J], sn[J], cs[J], G[2][NS];
+        CRL_UNROLL for (int j = 0; j < J; ++j) xu[2 * j] = Xc[(size_t)t * D + 2 * j];
+        Mdl::template angles<R>(xu, ang);
+        sincos_batch<J, R>(ang, sn, cs);
+        Mdl::template jac_trig<R>(xu, sn, cs, nullptr, nullptr, G);
+        CRL_UNROLL for (int i = 0; i < J; ++i) {
+            S[L::GT + t * 2 * J + i] = G[0][2 * i];
+            S[L::GT + t * 2 * J + J + i] = G[1][2 * i];
+        }
+    }
+    for (int e = lane; e < L::ZEND; e += 32) S[e] = R(0);
+    if (lane == 0) S[L::ONE] = R(1);
+    __syncwarp();
+    if (lane < 2 * J) S[L::GCUR + lane] = S[L::GT + (T - 1) * 2 * J + lane];
+
+    // ---- per-lane element descriptors
+    int a_o0[R1], a_o1[R1], a_dst[R1], a_kind[R1];
+    bool a_ok[R1];
+    CRL_UNROLL for (int r = 0; r < R1; ++r) {
+        const int e = lane + 32 * r;
+        a_ok[r] = e < N1;
+        if (e < NS * NS) {
+            const int i = e / NS, k = e % NS, odd = i & 1;
+            a_o0[r] = L::V + (i - odd) * NS + k;
+            a_o1[r] = L::V + i * NS + k;
+            a_kind[r] = odd ? CK_HPLUS : CK_PLAIN;
+            a_dst[r] = L::MA + e;
+        } else {
+            const int e2 = a_ok[r] ? e - NS * NS : 0;
+            const int a = e2 / NS, k = e2 % NS;
+            a_o0[r] = a_o1[r] = L::V + (2 * a + 1) * NS + k;
+            a_kind[r] = CK_HONLY;
+            a_dst[r] = L::MB + e2;
+        }
+    }
+    int b_o0[R2], b_o1[R2], b_kind[R2], b_dst[R2], b_xcol[R2];
+    int b_gai[R2], b_gas[R2], b_gaj[R2], b_gbi[R2], b_gbs[R2], b_gbj[R2];
+    bool b_ok[R2], b_g[R2], b_add[R2], b_const[R2];
+    R b_cbase[R2], b_cmul[R2];
+    CRL_UNROLL for (int r = 0; r < R2; ++r) {
+        const int e = lane + 32 * r;
+        b_ok[r] = e < N2;
+        b_g[r] = false; b_add[r] = false; b_const[r] = true;
+        b_cbase[r] = R(0); b_cmul[r] = R(0); b_xcol[r] = -1;
+        b_gai[r] = b_gas[r] = b_gaj[r] = b_gbi[r] = b_gbs[r] = b_gbj[r] = L::ONE;
+        b_o0[r] = b_o1[r] = L::ONE; b_kind[r] = CK_PLAIN; b_dst[r] = L::QX;
+        if (e < NP) {                                             // Qss(i, j), i <= j
+            int i, j;
+            coop_pair(e, NS, i, j);
+            b_kind[r] = (j & 1) ? CK_HPLUS : CK_PLAIN;
+            b_o1[r] = L::MA + i * NS + j;
+            b_o0[r] = (j & 1) ? b_o1[r] - 1 : b_o1[r];
+            b_g[r] = !(i & 1) && !(j & 1);
+            b_gai[r] = L::GCUR + i / 2; b_gas[r] = L::VYY; b_gaj[r] = L::GCUR + j / 2;
+            b_gbi[r] = L::GCUR + J + i / 2; b_gbs[r] = L::VYY + 1; b_gbj[r] = L::GCUR + J + j / 2;
+            b_add[r] = (i == j);
+            b_cbase[r] = (i & 1) ? R(cost_hess<Mdl>(1)) : R(cost_hess<Mdl>(0));
+            b_dst[r] = L::QX + i * NQ + j;
+        } else if (e < NP + M * NS) {                             // Qus(a, j)
+            const int e2 = e - NP, a = e2 / NS, j = e2 % NS;
+            b_kind[r] = (j & 1) ? CK_HPLUS : CK_PLAIN;
+            b_o1[r] = L::MB + a * NS + j;
+            b_o0[r] = (j & 1) ? b_o1[r] - 1 : b_o1[r];
+            b_dst[r] = L::QU + a * NQ + j;
+        } else if (e < NP + M * NS + NS) {                        // qs(i)
+            const int i = e - NP - M * NS;
+            b_kind[r] = (i & 1) ? CK_HPLUS : CK_PLAIN;
+            b_o1[r] = L::VS + i;
+            b_o0[r] = (i & 1) ? b_o1[r] - 1 : b_o1[r];
+            b_g[r] = !(i & 1);
+            b_gai[r] = L::VY; b_gas[r] = L::ONE; b_gaj[r] = L::GCUR + i / 2;
+            b_gbi[r] = L::VY + 1; b_gbs[r] = L::ONE; b_gbj[r] = L::GCUR + J + i / 2;
+            b_add[r] = true;
+            b_const[r] = !(i & 1);                                // weight 0 on the angles: gradient is the literal 0.0
+            b_cmul[r] = R(2.0 * Mdl::weight(1));
+            b_xcol[r] = (i & 1) ? i : -1;
+            b_dst[r] = L::QX + i * NQ + NS;
+        } else if (e < N2) {                                      // qu(a)
+            const int a = e - NP - M * NS - NS;
+            b_kind[r] = CK_HONLY;
+            b_o0[r] = b_o1[r] = L::VS + 2 * a + 1;
+            b_add[r] = true;
+            b_const[r] = false;
+            b_cmul[r] = R(2.0 * Mdl::weight(N));
+            b_xcol[r] = N + a;
+            b_dst[r] = L::QU + a * NQ + NS;
+        }
+    }
+    // stage 5: element (i, j), i <= j <= NS (j == NS: the gradient v)
+    int c_i = 0, c_j = 0;
+    const bool c_ok = lane < N5;
+    if (c_ok) coop_pair(lane, NQ, c_i, c_j);
+    const int c_base = L::QX + c_i * NQ + c_j;
+    const int c_dst1 = (c_j < NS) ? L::V + c_i * NS + c_j : L::VS + c_i;
+    const int c_dst2 = (c_j < NS) ? L::V + c_j * NS + c_i : c_dst1;
+    const int vy_y = lane - N5;                                   // lanes N5, N5+1 update vy, vyy
+    const bool vy_ok = vy_y >= 0 && vy_y < 2;
+    const int st_a = lane / NQ, st_j = lane % NQ;                 // lanes < M*NQ store K / k
+    const bool st_ok = lane < M * NQ;
+    const int lu_r = lane < NQ ? lane : NQ - 1;                   // right-hand-side column of this lane
+    const bool gc_ok = lane >= NQ && lane < NQ + 2 * J;           // lanes that copy the next G row
+
+    // row values needed by this lane (stage 2: x_i / u_a; stage 5: output entry and its target), one step ahead
+    R xin[R2], xin_n[R2], xv = R(0), xv_n = R(0), pv = R(0), pv_n = R(0);
+    CRL_UNROLL for (int r = 0; r < R2; ++r) {
+        xin[r] = R(0);
+        xin_n[r] = b_xcol[r] >= 0 ? Xc[(size_t)(T - 1) * D + b_xcol[r]] : R(0);
+    }
+    if (vy_ok) {
+        xv_n = Xc[(size_t)(T - 1) * D + NS + vy_y];
+        pv_n = prm.get(T - 1, vy_y);
+    }
+    __syncwarp();
+
+    for (int t = T - 1; t >= 0; --t) {
+        CRL_UNROLL for (int r = 0; r < R2; ++r) xin[r] = xin_n[r];
+        xv = xv_n;
+        pv = pv_n;
+        if (t > 0) {
+            CRL_UNROLL for (int r = 0; r < R2; ++r)
+                if (b_xcol[r] >= 0) xin_n[r] = Xc[(size_t)(t - 1) * D + b_xcol[r]];
+            if (vy_ok) {
+                xv_n = Xc[(size_t)(t - 1) * D + NS + vy_y];
+                pv_n = prm.get(t - 1, vy_y);
+            }
+        }
+        // ---- stage 1: MA = A^T V, MB = B^T V; Quu and its LU factors in every lane
+        CRL_UNROLL for (int r = 0; r < R1; ++r) {
+            const R v = coop_hsum<R>(S, a_o0[r], a_o1[r], a_kind[r], h);
+            if (a_ok[r]) S[a_dst[r]] = v;
+        }
+        R Quu[M][M];
+        CRL_UNROLL for (int a = 0; a < M; ++a)
+            CRL_UNROLL for (int b = 0; b < M; ++b) {
+                const R acc = (S[L::V + (2 * a + 1) * NS + 2 * b + 1] * h) * h;
+                Quu[a][b] = (a == b) ? R(cost_hess<Mdl>(N + a)) + acc : acc;
+            }
+        LuFactors<M, R> lu;
+        lu_factor<M, R>(Quu, lu);
+        __syncwarp();
+        // ---- stage 2: Qss, Qus, qs, qu
+        CRL_UNROLL for (int r = 0; r < R2; ++r) {
+            R acc = coop_hsum<R>(S, b_o0[r], b_o1[r], b_kind[r], h);
+            const R mga = S[b_gai[r]] * S[b_gas[r]];
+            const R mgb = S[b_gbi[r]] * S[b_gbs[r]];
+            R accg = fmadd(mga, S[b_gaj[r]], acc);
+            accg = fmadd(mgb, S[b_gbj[r]], accg);
+            acc = b_g[r] ? accg : acc;
+            const R base = b_const[r] ? b_cbase[r] : b_cmul[r] * xin[r];
+            const R out = b_add[r] ? base + acc : acc;
+            if (b_ok[r]) S[b_dst[r]] = out;
+        }
+        __syncwarp();
+        // ---- stage 3: gains, one right-hand-side column per lane; next step's G row
+        {
+            R b[M][1];
+            CRL_UNROLL for (int a = 0; a < M; ++a) b[a][0] = S[L::QU + a * NQ + lu_r];
+            lu_apply<M, 1, R>(lu, b);
+            if (lane < NQ) {
+                CRL_UNROLL for (int a = 0; a < M; ++a) S[L::KK + a * NQ + lane] = -b[a][0];
+            }
+            if (gc_ok && t > 0) S[L::GCUR + lane - NQ] = S[L::GT + (t - 1) * 2 * J + lane - NQ];
+        }
+        __syncwarp();
+        // ---- stage 5: V, v (W = K^T Quu recomputed per element), output block, K / k to global
+        {
+            R Ki[M], Kj[M], Ui[M], Uj[M], W[M];
+            CRL_UNROLL for (int a = 0; a < M; ++a) {
+                Ki[a] = S[L::KK + a * NQ + c_i];
+                Kj[a] = S[L::KK + a * NQ + c_j];
+                Ui[a] = S[L::QU + a * NQ + c_i];
+                Uj[a] = S[L::QU + a * NQ + c_j];
+            }
+            CRL_UNROLL for (int b = 0; b < M; ++b) {
+                R acc = Ki[0] * Quu[0][b];
+                CRL_UNROLL for (int a = 1; a < M; ++a) acc = fmadd(Ki[a], Quu[a][b], acc);
+                W[b] = acc;
+            }
+            R sij = Ui[0] * Kj[0], sji = Uj[0] * Ki[0], rr = W[0] * Kj[0];
+            CRL_UNROLL for (int a = 1; a < M; ++a) {
+                sij = fmadd(Ui[a], Kj[a], sij);
+                sji = fmadd(Uj[a], Ki[a], sji);
+                rr = fmadd(W[a], Kj[a], rr);
+            }
+            const R out = ((S[c_base] + sij) + sji) + rr;
+            const R kval = S[L::KK + (st_ok ? st_a * NQ + st_j : 0)];
+            if (c_ok) {
+                S[c_dst1] = out;
+                S[c_dst2] = out;
+            }
+            if (vy_ok) {
+                const R w2 = R(2.0 * Mdl::weight(NS));
+                S[L::VY + vy_y] = (-w2) * pv + w2 * xv;
+                S[L::VYY + vy_y] = R(cost_hess<Mdl>(NS));
+            }
+            if (st_ok) {
+                if (st_j < NS) Kb[(size_t)t * (M * NS) + st_a * NS + st_j] = kval;
+                else kb[(size_t)t * M + st_a] = kval;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Feed of a closed-loop rollout over row-major single-trajectory arrays that loads step t+1's
+// inputs while step t computes (one warp alone on an SM partition has nothing else to hide the
+// load latency with).
+template <class Mdl, class R>
+struct RowPrefetchFeed {
+    static constexpr int kKN = Mdl::NS;
+    const R* X;
+    const R* K;
+    const R* k;
+    int nsteps;
+    R nx[Mdl::NS], nu[Mdl::M], nK[Mdl::M * Mdl::NS], nk[Mdl::M];
+    __device__ RowPrefetchFeed(const R* X_, const R* K_, const R* k_) : X(X_), K(K_), k(k_), nsteps(0) {}
+    __device__ __forceinline__ void load(int t) {
+        const R* xr = X + (size_t)t * Mdl::D;
+        const R* Kr = K + (size_t)t * (Mdl::M * Mdl::NS);
+        const R* kr = k + (size_t)t * Mdl::M;
+        CRL_UNROLL for (int j = 0; j < Mdl::NS; ++j) nx[j] = xr[j];
+        CRL_UNROLL for (int a = 0; a < Mdl::M; ++a) nu[a] = xr[Mdl::N + a];
+        CRL_UNROLL for (int j = 0; j < Mdl::M * Mdl::NS; ++j) nK[j] = Kr[j];
+        CRL_UNROLL for (int a = 0; a < Mdl::M; ++a) nk[a] = kr[a];
+    }
+    __device__ void begin(int n) {
+        nsteps = n;
+        if (n > 0) load(0);
+    }
+    __device__ void end() {}
+    __device__ void row0(R* xu) const {
+        CRL_UNROLL for (int i = 0; i < Mdl::D; ++i) xu[i] = X[i];
+    }
+    __device__ void get(int t, R* xo, R* uo, R* Kc, R* kc) {
+        CRL_UNROLL for (int j = 0; j < Mdl::NS; ++j) xo[j] = nx[j];
+        CRL_UNROLL for (int a = 0; a < Mdl::M; ++a) uo[a] = nu[a];
+        CRL_UNROLL for (int j = 0; j < Mdl::M * Mdl::NS; ++j) Kc[j] = nK[j];
+        CRL_UNROLL for (int a = 0; a < Mdl::M; ++a) kc[a] = nk[a];
+        if (t + 1 < nsteps) load(t + 1);
+    }
+};
+
+}  // namespace crl

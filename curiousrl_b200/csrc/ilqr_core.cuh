@@ -246,45 +246,77 @@ CRL_HD void acc_kind(R& acc, bool& have, R val, int kind, double cst, R var) {
     have = true;
 }
 
-// In-place solve  a x = b  (M x M, NR right-hand sides) by LU with partial pivoting,
-// the algorithm behind np.linalg.solve / dgesv (ilqr_wrapper.py:246-247): first largest
-// |pivot| per column, reciprocal-scaled multipliers, no early-out on tiny or negative pivots.
-template <int M, int NR, class R>
-CRL_HD void lu_solve(R (&a)[M][M], R (&b)[M][NR]) {
-    R inv[M];
+// Solve  a x = b  (M x M, NR right-hand sides) by LU with partial pivoting, the algorithm
+// behind np.linalg.solve / dgesv (ilqr_wrapper.py:246-247): first largest |pivot| per column,
+// reciprocal-scaled multipliers, no early-out on tiny or negative pivots.
+// Split into the factorisation (depends on `a` only) and its application to right-hand sides, so
+// that the warp-cooperative path (ilqr_coop.cuh) can factor once per lane and apply the result to
+// one column per lane: per element the arithmetic is the same sequence in both forms.
+template <int M, class R>
+struct LuFactors {
+    R u[M][M];          // rows after elimination (upper triangle is U; the rest is not used)
+    R l[M][M];          // multipliers l[i][k], i > k
+    R inv[M];           // reciprocal pivots
+    bool sw[M][M];      // sw[k][i]: rows k and i were exchanged at step k (i > k)
+};
+
+template <int M, class R>
+CRL_HD void lu_factor(const R (&a)[M][M], LuFactors<M, R>& f) {
+    CRL_UNROLL for (int i = 0; i < M; ++i)
+        CRL_UNROLL for (int j = 0; j < M; ++j) f.u[i][j] = a[i][j];
     CRL_UNROLL for (int k = 0; k < M; ++k) {
         int p = k;
-        R best = fabs_(a[k][k]);
+        R best = fabs_(f.u[k][k]);
         CRL_UNROLL for (int i = k + 1; i < M; ++i) {
-            const R v = fabs_(a[i][k]);
+            const R v = fabs_(f.u[i][k]);
             if (v > best) { best = v; p = i; }
         }
         CRL_UNROLL for (int i = k + 1; i < M; ++i) {
             const bool sw = (p == i);
+            f.sw[k][i] = sw;
             CRL_UNROLL for (int j = 0; j < M; ++j) {
-                const R x = a[k][j], y = a[i][j];
-                a[k][j] = sw ? y : x;
-                a[i][j] = sw ? x : y;
+                const R x = f.u[k][j], y = f.u[i][j];
+                f.u[k][j] = sw ? y : x;
+                f.u[i][j] = sw ? x : y;
             }
+        }
+        f.inv[k] = R(1) / f.u[k][k];
+        CRL_UNROLL for (int i = k + 1; i < M; ++i) {
+            const R l = f.u[i][k] * f.inv[k];
+            f.l[i][k] = l;
+            CRL_UNROLL for (int j = k + 1; j < M; ++j) f.u[i][j] = fmadd(-l, f.u[k][j], f.u[i][j]);
+        }
+    }
+}
+
+template <int M, int NR, class R>
+CRL_HD void lu_apply(const LuFactors<M, R>& f, R (&b)[M][NR]) {
+    CRL_UNROLL for (int k = 0; k < M; ++k) {
+        CRL_UNROLL for (int i = k + 1; i < M; ++i) {
+            const bool sw = f.sw[k][i];
             CRL_UNROLL for (int r = 0; r < NR; ++r) {
                 const R x = b[k][r], y = b[i][r];
                 b[k][r] = sw ? y : x;
                 b[i][r] = sw ? x : y;
             }
         }
-        inv[k] = R(1) / a[k][k];
         CRL_UNROLL for (int i = k + 1; i < M; ++i) {
-            const R l = a[i][k] * inv[k];
-            CRL_UNROLL for (int j = k + 1; j < M; ++j) a[i][j] = fmadd(-l, a[k][j], a[i][j]);
-            CRL_UNROLL for (int r = 0; r < NR; ++r) b[i][r] = fmadd(-l, b[k][r], b[i][r]);
+            CRL_UNROLL for (int r = 0; r < NR; ++r) b[i][r] = fmadd(-f.l[i][k], b[k][r], b[i][r]);
         }
     }
     CRL_UNROLL for (int j = M - 1; j >= 0; --j) {
-        CRL_UNROLL for (int r = 0; r < NR; ++r) b[j][r] = b[j][r] * inv[j];
+        CRL_UNROLL for (int r = 0; r < NR; ++r) b[j][r] = b[j][r] * f.inv[j];
         CRL_UNROLL for (int i = 0; i < j; ++i) {
-            CRL_UNROLL for (int r = 0; r < NR; ++r) b[i][r] = fmadd(-a[i][j], b[j][r], b[i][r]);
+            CRL_UNROLL for (int r = 0; r < NR; ++r) b[i][r] = fmadd(-f.u[i][j], b[j][r], b[i][r]);
         }
     }
+}
+
+template <int M, int NR, class R>
+CRL_HD void lu_solve(const R (&a)[M][M], R (&b)[M][NR]) {
+    LuFactors<M, R> f;
+    lu_factor<M, R>(a, f);
+    lu_apply<M, NR, R>(f, b);
 }
 
 // Value-function state carried down the horizon.  Because the output entries y never feed

@@ -22,6 +22,7 @@
 
 #include "../../include/curiousrl_b200.h"
 #include "ilqr_core.cuh"
+#include "ilqr_coop.cuh"
 
 namespace crl {
 
@@ -309,6 +310,16 @@ struct TileRowFeed {
 };
 
 // ------------------------------------------------------------------------------ persistent solve
+// One straggler handed from lane mode to the cooperative finishers (ilqr_coop.cuh).
+struct QueueEntry {
+    long long traj;                // index in the batch
+    const void* src;               // element (t = 0, c = 0) of its current trajectory: a tile column, stride 32
+    double J_last;
+    int it;                        // iterations done so far
+    int ready;                     // published (written last, after a fence)
+};
+static_assert(sizeof(QueueEntry) == 32, "queue entries are 32 bytes");
+
 template <class R>
 struct SolveArgs {
     ProblemDev<R> pb;
@@ -325,12 +336,201 @@ struct SolveArgs {
     int8_t* alpha_trace;
     R* ws;                         // [slots][slot_elems]
     long long slot_elems;          // reals per warp slot
-    unsigned long long* counter;   // next unassigned trajectory
+    unsigned long long* ctl;       // control block (zeroed per launch): see kCtl*
+    QueueEntry* queue;             // straggler queue, one entry per lane of the grid
+    int coop_threshold;            // a drained warp with <= this many live trajectories hands them over; < 0 = never
 };
+
+// Control block words.
+constexpr int kCtlNext = 0;        // next unassigned trajectory of the batch
+constexpr int kCtlTail = 1;        // straggler queue: entries reserved by producers
+constexpr int kCtlHead = 2;        // straggler queue: entries claimed by finishers
+constexpr int kCtlDone = 3;        // warps that have left lane mode (and published their stragglers)
+constexpr size_t kCtlBytes = 256;
+
+// Optional phase timers (development builds, -DCRL_PHASE_TIMERS): lane 0 of every warp adds the
+// SM cycles it spent per phase to control-block words kCtlTimers + phase.
+constexpr int kCtlTimers = 8;
+enum Phase : int { PH_REFILL = 0, PH_BACKWARD, PH_LINESEARCH, PH_RETIRE, PH_COOP_WAIT, PH_COOP_GATHER, PH_COOP_BACKWARD,
+                   PH_COOP_LINESEARCH, PH_COOP_OUTPUT, PH_COUNT };
+#ifdef CRL_PHASE_TIMERS
+struct PhaseTimer {
+    long long acc[PH_COUNT] = {};
+    long long t0;
+    __device__ static long long now() {
+        long long t;
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+        return t;
+    }
+    __device__ PhaseTimer() : t0(now()) {}
+    __device__ void lap(int phase) {
+        const long long t = now();
+        acc[phase] += t - t0;
+        t0 = t;
+    }
+    __device__ void flush(unsigned long long* ctl, int lane) {
+        if (lane == 0)
+            for (int i = 0; i < PH_COUNT; ++i) atomicAdd(ctl + kCtlTimers + i, (unsigned long long)acc[i]);
+    }
+};
+#else
+struct PhaseTimer {
+    __device__ void lap(int) {}
+    __device__ void flush(unsigned long long*, int) {}
+};
+#endif
 
 template <class Mdl>
 __host__ __device__ constexpr long long slot_reals(int T) {
     return (long long)T * 32 * (2 * Mdl::D + Mdl::M * Mdl::NS + Mdl::M);
+}
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+    return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+
+// Finishes one straggler with the whole warp: gathers its current trajectory from the producer's
+// tile column into row-major scratch, then iterates {cooperative backward pass, one-step-size-per-
+// lane line search, accept / stop} to the end and writes the results.  xfree: 32 trajectory
+// buffers [T][D]; gfree: K [T][M*NS] then k [T][M]; S: the warp's shared-memory area.
+template <class Mdl, class R>
+__device__ void coop_finish(const SolveArgs<R>& a, const QueueEntry& ent, R* xfree, R* gfree, R* S, int lane,
+                            PhaseTimer& tm) {
+    constexpr int M = Mdl::M, D = Mdl::D, NS = Mdl::NS;
+    const int T = a.pb.T;
+    const size_t TD = (size_t)T * D;
+    R* const Kb = gfree;
+    R* const kb = gfree + (size_t)T * M * NS;
+    const long long traj = ent.traj;
+    const ParamRef<R> prm = a.pb.prm(traj);
+    double J_last = ent.J_last;
+    int it = ent.it;
+    {
+        const R* src = reinterpret_cast<const R*>(ent.src);
+        for (int e = lane; e < T * D; e += 32) xfree[e] = __ldcg(src + (size_t)e * 32);
+    }
+    __syncwarp();
+    tm.lap(PH_COOP_GATHER);
+    int curbuf = 0;
+    const int tries = (a.op.ls_method == CRL_LS_NONE) ? 1 : a.op.max_ls;
+    const bool feas = a.op.ls_method == CRL_LS_FEASIBILITY;
+    while (true) {
+        const R* Xc = xfree + curbuf * TD;
+        coop_backward<Mdl, R>(Xc, prm, T, Kb, kb, S, lane);
+        __syncwarp();
+        tm.lap(PH_COOP_BACKWARD);
+        bool accepted = false;
+        double J_new = J_last;
+        int taken = -1, newbuf = curbuf;
+        for (int a0 = 0; a0 < tries && !accepted; a0 += 31) {
+            const int idx = a0 + lane;
+            const bool work = lane < 31 && idx < tries;
+            double Jt = 0.0;
+            bool ok = false;
+            if (work) {
+                double al = 1.0;
+                for (int i = 0; i < idx; ++i) al = al * a.op.gamma;
+                const int buf = lane < curbuf ? lane : lane + 1;
+                RowPrefetchFeed<Mdl, R> feed(Xc, Kb, kb);
+                const View<R, D, 1> Xn{xfree + buf * TD};
+                Jt = rollout_closed_f<Mdl, R>(feed, (R)al, prm, a.pb.ub, T, Xn);
+                ok = (a.op.ls_method == CRL_LS_NONE) || ls_accept(Jt, J_last, feas);
+            }
+            const unsigned okm = __ballot_sync(kFull, ok);
+            if (okm != 0u) {
+                const int w = __ffs(okm) - 1;                    // lowest lane = largest step size
+                accepted = true;
+                taken = a0 + w;
+                J_new = __shfl_sync(kFull, Jt, w);
+                newbuf = w < curbuf ? w : w + 1;
+            }
+        }
+        __syncwarp();
+        tm.lap(PH_COOP_LINESEARCH);
+        const bool stop = stop_test(J_new, J_last, a.op.criterion, a.op.stop_method == CRL_STOP_RELATIVE);
+        J_last = J_new;
+        if (lane == 0) {
+            if (a.J_trace) a.J_trace[traj * a.op.max_iter + it] = J_new;
+            if (a.alpha_trace) a.alpha_trace[traj * a.op.max_iter + it] = (int8_t)taken;
+        }
+        ++it;
+        curbuf = newbuf;
+        if ((stop && a.op.check_stop) || it >= a.op.max_iter) {
+            if (lane == 0) {
+                a.J_out[traj] = J_last;
+                a.iters_out[traj] = it;
+                a.conv_out[traj] = (stop && a.op.check_stop) ? 1 : 0;
+            }
+            if (a.X_out) {
+                const R* src = xfree + curbuf * TD;
+                R* dst = a.X_out + traj * TD;
+                for (int e = lane; e < T * D; e += 32) dst[e] = src[e];
+            }
+            tm.lap(PH_COOP_OUTPUT);
+            return;
+        }
+    }
+}
+
+// Tail of the solve kernel, entered by every warp exactly once when it leaves lane mode: publishes
+// the warp's live trajectories (mask `live`; each lane's current trajectory is column `lane` of
+// `Xcol0`) on the straggler queue, then serves the queue until every warp of the grid has left
+// lane mode and the queue is empty.
+template <class Mdl, class R>
+__device__ void coop_tail(const SolveArgs<R>& a, bool live, long long traj, int it, double J_last, const R* my_col,
+                          R* xfree, R* gfree, R* S, unsigned total_warps, int lane, PhaseTimer& tm) {
+    const unsigned live_mask = __ballot_sync(kFull, live);
+    if (live_mask != 0u) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.ctl + kCtlTail, (unsigned long long)__popc(live_mask));
+        base = __shfl_sync(kFull, base, 0);
+        if (live) {
+            QueueEntry* e = a.queue + base + __popc(live_mask & ((1u << lane) - 1u));
+            e->traj = traj;
+            e->src = my_col;
+            e->J_last = J_last;
+            e->it = it;
+            __threadfence();
+            *reinterpret_cast<volatile int*>(&e->ready) = 1;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence();
+        atomicAdd(a.ctl + kCtlDone, 1ull);
+    }
+    tm.lap(PH_RETIRE);
+    while (true) {
+        unsigned long long idx = 0;
+        int got = 0;
+        if (lane == 0) {
+            idx = atomicAdd(a.ctl + kCtlHead, 1ull);
+            const volatile int* rdy = &a.queue[idx].ready;
+            const bool in_range = idx < (unsigned long long)total_warps * 32ull;
+            while (true) {
+                if (in_range && *rdy != 0) { got = 1; break; }
+                if (ld_volatile_u64(a.ctl + kCtlDone) >= (unsigned long long)total_warps) {
+                    __threadfence();
+                    if (in_range && *rdy != 0) got = 1;       // published before its producer reported done
+                    break;
+                }
+                __nanosleep(1000);
+            }
+            __threadfence();
+        }
+        got = __shfl_sync(kFull, got, 0);
+        tm.lap(PH_COOP_WAIT);
+        if (!got) return;
+        idx = __shfl_sync(kFull, idx, 0);
+        QueueEntry ent;
+        const QueueEntry* qe = a.queue + idx;
+        ent.traj = __ldcg(&qe->traj);
+        ent.src = (const void*)(uintptr_t)__ldcg(reinterpret_cast<const unsigned long long*>(&qe->src));
+        ent.J_last = __ldcg(&qe->J_last);
+        ent.it = __ldcg(&qe->it);
+        coop_finish<Mdl, R>(a, ent, xfree, gfree, S, lane, tm);
+        __syncwarp();
+    }
 }
 
 // WARPS = warps per CTA, MINB = resident CTAs per SM to compile for.  SYNC = true phase-locks the
@@ -341,6 +541,7 @@ __host__ __device__ constexpr long long slot_reals(int T) {
 template <class Mdl, class R, int WARPS, int MINB, bool SYNC>
 __global__ void __launch_bounds__(WARPS * 32, MINB) solve_kernel(SolveArgs<R> a) {
     constexpr int N = Mdl::N, M = Mdl::M, D = Mdl::D, NS = Mdl::NS;
+    constexpr bool kCoop = CoopSupport<Mdl>::value;
     const int lane = threadIdx.x & 31;
     const long long slot = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int T = a.pb.T;
@@ -369,13 +570,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) solve_kernel(SolveArgs<R> a)
     int pred = 0;                // step index this lane's trajectory accepted last (line-search guess)
     double J_last = 0.0;
     ParamRef<R> prm{a.pb.params, 0};
+    PhaseTimer tm;
 
     while (true) {
         // ---- refill idle lanes from the global queue
         const unsigned need = __ballot_sync(kFull, traj < 0);
         if (need != 0u && !exhausted) {
             unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(a.counter, (unsigned long long)__popc(need));
+            if (lane == 0) base = atomicAdd(a.ctl + kCtlNext, (unsigned long long)__popc(need));
             base = __shfl_sync(kFull, base, 0);
             if (base + __popc(need) >= (unsigned long long)a.pb.B) exhausted = true;
             if (traj < 0) {
@@ -393,14 +595,29 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) solve_kernel(SolveArgs<R> a)
             }
         }
         const bool active = traj >= 0;
+        if (kCoop && a.coop_threshold >= 0 && !exhausted) {
+            // a warp with no idle lane does not visit the queue: look at the counter instead
+            unsigned long long nxt = 0;
+            if (lane == 0) nxt = ld_volatile_u64(a.ctl + kCtlNext);
+            nxt = __shfl_sync(kFull, nxt, 0);
+            if (nxt >= (unsigned long long)a.pb.B) exhausted = true;
+        }
         if (SYNC) {
-            if (!__syncthreads_or(active)) break;           // CTA-uniform exit; also aligns the warps
+            const int live = __syncthreads_count(active);   // CTA-uniform; also aligns the warps
+            if (live == 0) break;
+            if (kCoop && a.coop_threshold >= 0) {
+                // queue empty and few trajectories left in this CTA: hand them to the finishers
+                if (__syncthreads_and(exhausted) && live <= a.coop_threshold * WARPS) break;
+            }
         } else {
-            if (!__any_sync(kFull, active)) break;
+            const unsigned live = __ballot_sync(kFull, active);
+            if (live == 0u) break;
+            if (kCoop && a.coop_threshold >= 0 && exhausted && __popc(live) <= a.coop_threshold) break;
         }
 
         const View<R, D, 32> Xc = cur ? Xbuf1 : Xbuf0;
         const View<R, D, 32> Xn = cur ? Xbuf0 : Xbuf1;
+        tm.lap(PH_REFILL);
 
         // ---- backward pass: K, k for every active lane
         const unsigned act_mask = __ballot_sync(kFull, active);
@@ -409,6 +626,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) solve_kernel(SolveArgs<R> a)
             backward_fused_f<Mdl, R, NS>(rows, prm, T, Kv, kv);
         }
         if (SYNC) __syncthreads();
+        tm.lap(PH_BACKWARD);
 
         // ---- line search: first improving alpha = 1, g, g^2, ...
         bool accepted = false;
@@ -417,7 +635,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) solve_kernel(SolveArgs<R> a)
         const int tries = (a.op.ls_method == CRL_LS_NONE) ? 1 : a.op.max_ls;
         const bool feas = a.op.ls_method == CRL_LS_FEASIBILITY;
         const unsigned act = __ballot_sync(kFull, active);
-        if (exhausted && __popc(act) <= kCoopMax) {
+        if (!kCoop && exhausted && __popc(act) <= kCoopMax) {
             // Straggler mode (queue empty, few trajectories left in this warp): the line search of
             // one trajectory at a time is spread over the idle lanes, one step size per lane, so a
             // whole line search costs one rollout of latency instead of up to max_line_search.
@@ -532,6 +750,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) solve_kernel(SolveArgs<R> a)
             }
         }
         if (accepted) pred = taken;
+        tm.lap(PH_LINESEARCH);
 
         // ---- stop test, bookkeeping, retirement
         bool finished = false;
@@ -574,7 +793,20 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) solve_kernel(SolveArgs<R> a)
         }
         if (finished) traj = -1;
         cur ^= 1;
+        tm.lap(PH_RETIRE);
     }
+
+    if constexpr (kCoop) {
+      if (a.coop_threshold >= 0) {
+        // Every warp reports to the straggler queue exactly once (with its live trajectories, which
+        // sit in tile `cur`) and then serves it; the other X tile and the gain tiles are its scratch.
+        const View<R, D, 32> Xc = cur ? Xbuf1 : Xbuf0;
+        R* const xfree = (cur ? Xbuf0 : Xbuf1).base - lane;
+        R* const gfree = Kv.base - lane;
+        coop_tail<Mdl, R>(a, traj >= 0, traj, it, J_last, Xc.base, xfree, gfree, stage_sm, gridDim.x * WARPS, lane, tm);
+      }
+    }
+    tm.flush(a.ctl, lane);
 }
 
 // ------------------------------------------------------------------------------ host side
@@ -619,7 +851,7 @@ static int check_problem(const crl_problem_t* p) {
 
 static int check_opts(const crl_solver_opts_t* o) {
     if (!o) return CRL_ERR_BAD_ARGUMENT;
-    if (o->max_iter < 0 || o->max_line_search < 0) return CRL_ERR_BAD_ARGUMENT;
+    if (o->max_iter < 0 || o->max_line_search < 0 || o->reserved2 != 0) return CRL_ERR_BAD_ARGUMENT;
     if (o->reserved != 0 && !(o->reserved >= 2 && o->reserved <= 4) && o->reserved != 11 && o->reserved != 12)
         return CRL_ERR_BAD_ARGUMENT;
     if (o->line_search_method < CRL_LS_VANILLA || o->line_search_method > CRL_LS_NONE) return CRL_ERR_BAD_ARGUMENT;
@@ -654,9 +886,32 @@ struct DeviceScope {
     }
 };
 
+static size_t queue_bytes(size_t slots) { return (slots * 32 * sizeof(QueueEntry) + 255) & ~(size_t)255; }
+
+// Per-warp live-trajectory count at or below which a drained warp hands its trajectories to the
+// cooperative finishers: opts->coop_threshold (0 = default, < 0 = off), off if the model has no
+// cooperative path or its shared-memory tables do not fit the warp's staging area at this horizon.
+template <class Mdl, class R>
+static int coop_threshold_for(const crl_solver_opts_t* o, int T) {
+    if (!CoopSupport<Mdl>::value || o->coop_threshold < 0) return -1;
+    if (CoopLayout<Mdl>::reals(T) > 2 * StageLayout<Mdl, R>::STAGE) return -1;
+    const int th = o->coop_threshold == 0 ? 8 : o->coop_threshold;
+    return th > 32 ? 32 : th;
+}
+
 static unsigned blocks_for(long long work) { return (unsigned)((work + kBlock - 1) / kBlock); }
 
 // model x dtype dispatch: the body (variadic, may contain commas) sees `Mdl` and `R`
+#ifdef CRL_DEV_FAST   // development builds: ThreeLink / float64 only (compiles in a fraction of the time)
+#define CRL_DISPATCH(model, dtype, ...)                                                  \
+    do {                                                                                 \
+        if ((dtype) == CRL_F64 && (model) == CRL_THREE_LINK) {                           \
+            using R = double;                                                            \
+            using Mdl = ThreeLink;                                                       \
+            __VA_ARGS__;                                                                 \
+        }                                                                                \
+    } while (0)
+#else
 #define CRL_DISPATCH(model, dtype, ...)                                                  \
     do {                                                                                 \
         if ((dtype) == CRL_F64) {                                                        \
@@ -675,6 +930,7 @@ static unsigned blocks_for(long long work) { return (unsigned)((work + kBlock - 
             }                                                                            \
         }                                                                                \
     } while (0)
+#endif
 
 // Launch configurations of the solve kernel.  opts->reserved selects one (0 = default):
 //   2, 3, 4 : 4 warps per CTA, that many resident CTAs per SM, warps free-running
@@ -706,6 +962,13 @@ struct SolveVariant {
     }
 };
 
+#ifdef CRL_DEV_FAST
+#define CRL_SOLVE_VARIANT(v, ...)                                                  \
+    switch (v) {                                                                   \
+        case 12: { using V = SolveVariant<Mdl, R, 4, 2, true>; __VA_ARGS__; } break;  \
+        default: break;                                                            \
+    }
+#else
 #define CRL_SOLVE_VARIANT(v, ...)                                                  \
     switch (v) {                                                                   \
         case 2: { using V = SolveVariant<Mdl, R, 4, 2, false>; __VA_ARGS__; } break;  \
@@ -715,6 +978,7 @@ struct SolveVariant {
         case 12: { using V = SolveVariant<Mdl, R, 4, 2, true>; __VA_ARGS__; } break;  \
         default: break;                                                            \
     }
+#endif
 
 // grid size and warps per CTA of the configuration `variant` (0 = default); grid < 0 on error
 template <class Mdl, class R>
@@ -897,7 +1161,8 @@ size_t crl_solve_workspace_bytes(const crl_problem_t* prob, const crl_solver_opt
     if (grid <= 0) return 0;
     const size_t elem = prob->dtype == CRL_F64 ? 8 : 4;
     const size_t slots = (size_t)grid * warps;
-    return 256 + slots * (size_t)reals * elem;     // first 256 bytes: the work counter
+    // control block, straggler queue (one entry per lane of the grid), warp slots
+    return kCtlBytes + queue_bytes(slots) + slots * (size_t)reals * elem;
 }
 
 int crl_solve(const crl_problem_t* prob, const crl_solver_opts_t* opts, const void* x0, const void* u0,
@@ -917,7 +1182,13 @@ int crl_solve(const crl_problem_t* prob, const crl_solver_opts_t* opts, const vo
     DeviceScope scope(x0);
     if (scope.status) return scope.status;
     cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(workspace, 0, 256, s);
+    size_t qbytes = 0;
+    {
+        int grid = 0, warps = 0;
+        CRL_DISPATCH(prob->model, prob->dtype, (solve_config<Mdl, R>(opts->grid_blocks, opts->reserved, &grid, &warps)));
+        qbytes = queue_bytes((size_t)grid * warps);
+    }
+    cudaError_t e = cudaMemsetAsync(workspace, 0, kCtlBytes + qbytes, s);   // counters and the queue's ready flags
     if (e != cudaSuccess) return cuda_status(e);
     CRL_DISPATCH(prob->model, prob->dtype, {
         SolveArgs<R> a;
@@ -933,8 +1204,10 @@ int crl_solve(const crl_problem_t* prob, const crl_solver_opts_t* opts, const vo
         a.conv_out = converged;
         a.J_trace = J_trace;
         a.alpha_trace = alpha_trace;
-        a.counter = (unsigned long long*)workspace;
-        a.ws = (R*)((char*)workspace + 256);
+        a.ctl = (unsigned long long*)workspace;
+        a.queue = (QueueEntry*)((char*)workspace + kCtlBytes);
+        a.ws = (R*)((char*)workspace + kCtlBytes + qbytes);
+        a.coop_threshold = coop_threshold_for<Mdl, R>(opts, prob->horizon);
         a.slot_elems = slot_reals<Mdl>(prob->horizon);
         int grid = 0, warps = 0;
         solve_config<Mdl, R>(opts->grid_blocks, opts->reserved, &grid, &warps);

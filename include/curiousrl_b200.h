@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CRL_ABI_VERSION 1
+#define CRL_ABI_VERSION 2
 
 typedef void* crl_stream_t; /* cudaStream_t */
 
@@ -72,7 +72,12 @@ typedef struct crl_solver_opts {
     int32_t line_search_method; /* enum crl_line_search */
     int32_t stopping_method;    /* enum crl_stopping    */
     int32_t grid_blocks;        /* 0 = auto: resident CTAs per SM x SM count                   */
-    int32_t reserved;
+    int32_t reserved;           /* launch configuration of the solve kernel, 0 = default       */
+    int32_t coop_threshold;     /* once the batch queue is empty, a warp with at most this many
+                                   unfinished trajectories hands them to the warp-cooperative
+                                   finishers (one warp per trajectory): 0 = default (8), < 0 = never.
+                                   Scheduling only - results do not depend on it.                */
+    int32_t reserved2;          /* must be 0                                                   */
 } crl_solver_opts_t;
 
 int crl_abi_version(void);

@@ -85,7 +85,7 @@ def test_forward_pass_decisions(golden, tag):
     g = golden(tag)
     dev = device_model(g)
     tgt = g["default_target"]
-    opts = _native.SolverOpts(1, 1, 1e-6, int(g["max_line_search"]), 0.5, 0, 0, 0, 0)
+    opts = _native.SolverOpts(1, 1, 1e-6, int(g["max_line_search"]), 0.5, 0, 0, 0, 0, 0, 0)
     for it in g["stage_iters"]:
         pre = "stage%d_" % it
         Xn, Jn, aidx, stop = dev.forward_pass(opts, g[pre + "X"][None], g[pre + "K"][None], g[pre + "k"][None],

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), "symbol %s declared in the header is not exported" % name
     assert sorted(_native.EXPORTS) == names
-    assert lib.crl_abi_version() == 1
+    assert lib.crl_abi_version() == _native.ABI_VERSION == 2
 
 
 def test_model_tables_and_status_strings():
@@ -52,7 +52,7 @@ def test_argument_validation_happens_before_any_cuda_call():
         return _native.Problem(d["model"], d["dtype"], d["batch"], d["horizon"], d["params_stride_t"],
                                d["params_stride_b"], d["params"], d["u_lo"], d["u_hi"])
 
-    opts = _native.SolverOpts(10, 1, 1e-6, 10, 0.5, 0, 0, 0, 0)
+    opts = _native.SolverOpts(10, 1, 1e-6, 10, 0.5, 0, 0, 0, 0, 0, 0)
     dummy = ctypes.c_void_p(0x1000)
     assert lib.crl_rollout(None, dummy, None, 0, dummy, None, None) == -1
     assert lib.crl_rollout(prob(model=5), dummy, None, 0, dummy, None, None) == -2
@@ -63,7 +63,7 @@ def test_argument_validation_happens_before_any_cuda_call():
     assert lib.crl_rollout(prob(u_lo=1.0, u_hi=-1.0), dummy, None, 0, dummy, None, None) == -1
     assert lib.crl_rollout(prob(batch=0), None, None, 0, None, None, None) == 0          # empty batch: nothing to do
     assert lib.crl_rollout(prob(), None, None, 0, dummy, None, None) == -1               # missing x0
-    bad_opts = _native.SolverOpts(10, 1, 1e-6, 10, 0.5, 7, 0, 0, 0)
+    bad_opts = _native.SolverOpts(10, 1, 1e-6, 10, 0.5, 7, 0, 0, 0, 0, 0)
     assert lib.crl_forward_pass(prob(), ctypes.byref(bad_opts), dummy, dummy, dummy, dummy, dummy, dummy, dummy, dummy,
                                 None) == -1
     assert lib.crl_backward_dense(5, 2, 0, 1, 10, dummy, dummy, dummy, dummy, dummy, None) == -2

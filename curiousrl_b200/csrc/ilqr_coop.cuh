@@ -8,8 +8,8 @@
 // it takes one straggler at a time and iterates it with all 32 lanes,
 //   * backward pass (ilqr_wrapper.py:232-256): every matrix element of the Riccati step is owned
 //     by one lane, operands are exchanged through shared memory (4 warp barriers per time step),
-//     the 3x3 / 2x2 pivoted LU of Quu is factored redundantly by every lane while the Q blocks are
-//     formed and applied to one right-hand-side column per lane;
+//     the 3x3 / 2x2 pivoted LU of Quu is factored by the lanes that then apply it to one
+//     right-hand-side column each; several trajectories can be stepped together (coop_backward<NT>);
 //   * line search (ilqr_wrapper.py:74-100): one step size per lane, all candidates at once.
 // Per element the arithmetic is the SAME operation sequence as the lane-per-trajectory code in
 // ilqr_core.cuh (riccati_step / rollout_closed_f), so a trajectory's result does not depend on
@@ -27,7 +27,7 @@ template <class Mdl> struct CoopSupport { static constexpr bool value = false; }
 template <> struct CoopSupport<TwoLink> { static constexpr bool value = true; };
 template <> struct CoopSupport<ThreeLink> { static constexpr bool value = true; };
 
-// Shared-memory layout (in reals) of one warp's cooperative backward pass.
+// Shared-memory layout (in reals) of the cooperative backward pass of ONE trajectory.
 template <class Mdl>
 struct CoopLayout {
     static constexpr int NS = Mdl::NS, M = Mdl::M, J = Mdl::M, NQ = Mdl::NS + 1;
@@ -43,8 +43,10 @@ struct CoopLayout {
     static constexpr int QX = MB + M * NS;            // NS x NQ [Qss (upper triangle) | qs]
     static constexpr int QU = QX + NS * NQ;           // M x NQ  [Qus | qu]
     static constexpr int KK = QU + M * NQ;            // M x NQ  [K | k]
-    static constexpr int GT = (KK + M * NQ + 1) & ~1; // [T][2J] G entries of every time step
-    __host__ __device__ static constexpr int reals(int T) { return GT + T * 2 * J; }
+    static constexpr int QUU = KK + M * NQ;           // M x M   Quu (before factorisation)
+    static constexpr int DUMMY = QUU + M * M;         // where lanes without an element of a stage write
+    static constexpr int SZ = (DUMMY + 2) & ~1;       // reals per trajectory
+    static constexpr int GROW = 2 * J;                // reals per time step of the global G table
 };
 
 // i <= j < n enumerated row by row: element e of the upper triangle of an n-column matrix
@@ -71,37 +73,57 @@ __device__ __forceinline__ R coop_hsum(const R* S, int o0, int o1, int kind, R h
     return kind == CK_PLAIN ? m1 : (kind == CK_HPLUS ? p + m1 : p);
 }
 
-// Backward pass of one trajectory (row-major Xc [T][D]) by the whole warp; writes K [T][M*NS]
-// and k [T][M] (row-major, global).  S = this warp's shared-memory area (CoopLayout).
-template <class Mdl, class R>
-__device__ void coop_backward(const R* Xc, const ParamRef<R>& prm, int T, R* Kb, R* kb, R* S, int lane) {
+// One trajectory of a cooperative backward pass: its current trajectory (row-major [T][D]), cost
+// parameters, outputs K [T][M*NS], k [T][M] (row-major) and a scratch table [T][2J] for the variable
+// Jacobian entries - all global.  on = false: the slot is empty; its pointers must still be valid
+// scratch (the pass runs branch-free over all NT slots and ignores what an empty one produces).
+template <class R>
+struct CoopTraj {
+    const R* X;
+    ParamRef<R> prm;
+    R* K;
+    R* k;
+    R* G;
+    bool on;
+};
+
+// Backward pass of NT trajectories by one warp, time step by time step for all of them together:
+// the NT Riccati recursions are independent dependency chains, so interleaving them fills the issue
+// slots a single chain leaves empty (one chain alone uses ~1/4 of them).  S = this warp's
+// shared-memory area, NT * CoopLayout::SZ reals.
+template <class Mdl, class R, int NT>
+__device__ void coop_backward(const CoopTraj<R> (&tr)[NT], int T, R* S, int lane) {
     using L = CoopLayout<Mdl>;
     constexpr int NS = Mdl::NS, M = Mdl::M, J = Mdl::M, N = Mdl::N, D = Mdl::D, NQ = NS + 1;
     constexpr int N1 = NS * NS + M * NS, R1 = (N1 + 31) / 32;                     // stage 1: MA, MB
     constexpr int NP = NS * (NS + 1) / 2;                                          // upper-triangle pairs
     constexpr int N2 = NP + M * NS + NS + M, R2 = (N2 + 31) / 32;                 // stage 2: Qss, Qus, qs, qu
     constexpr int N5 = NP + NS;                                                    // stage 5: V, v
-    static_assert(N5 + 2 <= 32 && NQ + 2 * J <= 32 && M * NQ <= 32, "element-to-lane mapping needs <= 32 lanes per stage");
+    static_assert(N5 + 2 <= 32 && NT * NQ <= 32 && NT * 2 * J <= 32 && M * NQ <= 32,
+                  "element-to-lane mapping needs <= 32 lanes per stage");
     const R h = R(kH);
 
-    // ---- G table: lanes take time steps lane, lane + 32, ...
-    for (int t = lane; t < T; t += 32) {
-        R xu[D], ang[J], sn[J], cs[J], G[2][NS];
-        CRL_UNROLL for (int j = 0; j < J; ++j) xu[2 * j] = Xc[(size_t)t * D + 2 * j];
-        Mdl::template angles<R>(xu, ang);
-        sincos_batch<J, R>(ang, sn, cs);
-        Mdl::template jac_trig<R>(xu, sn, cs, nullptr, nullptr, G);
-        CRL_UNROLL for (int i = 0; i < J; ++i) {
-            S[L::GT + t * 2 * J + i] = G[0][2 * i];
-            S[L::GT + t * 2 * J + J + i] = G[1][2 * i];
+    // ---- G tables: lanes take time steps lane, lane + 32, ...
+    CRL_UNROLL for (int q = 0; q < NT; ++q) {
+        for (int t = lane; t < T; t += 32) {
+            R xu[D], ang[J], sn[J], cs[J], G[2][NS];
+            CRL_UNROLL for (int j = 0; j < J; ++j) xu[2 * j] = tr[q].X[(size_t)t * D + 2 * j];
+            Mdl::template angles<R>(xu, ang);
+            sincos_batch<J, R>(ang, sn, cs);
+            Mdl::template jac_trig<R>(xu, sn, cs, nullptr, nullptr, G);
+            CRL_UNROLL for (int i = 0; i < J; ++i) {
+                tr[q].G[(size_t)t * L::GROW + i] = G[0][2 * i];
+                tr[q].G[(size_t)t * L::GROW + J + i] = G[1][2 * i];
+            }
         }
     }
-    for (int e = lane; e < L::ZEND; e += 32) S[e] = R(0);
-    if (lane == 0) S[L::ONE] = R(1);
+    CRL_UNROLL for (int q = 0; q < NT; ++q) {
+        for (int e = lane; e < L::ZEND; e += 32) S[q * L::SZ + e] = R(0);
+        if (lane == 0) S[q * L::SZ + L::ONE] = R(1);
+    }
     __syncwarp();
-    if (lane < 2 * J) S[L::GCUR + lane] = S[L::GT + (T - 1) * 2 * J + lane];
 
-    // ---- per-lane element descriptors
+    // ---- per-lane element descriptors (the same for every trajectory)
     int a_o0[R1], a_o1[R1], a_dst[R1], a_kind[R1];
     bool a_ok[R1];
     CRL_UNROLL for (int r = 0; r < R1; ++r) {
@@ -118,7 +140,7 @@ __device__ void coop_backward(const R* Xc, const ParamRef<R>& prm, int T, R* Kb,
             const int a = e2 / NS, k = e2 % NS;
             a_o0[r] = a_o1[r] = L::V + (2 * a + 1) * NS + k;
             a_kind[r] = CK_HONLY;
-            a_dst[r] = L::MB + e2;
+            a_dst[r] = a_ok[r] ? L::MB + e2 : L::DUMMY;
         }
     }
     int b_o0[R2], b_o1[R2], b_kind[R2], b_dst[R2], b_xcol[R2];
@@ -131,7 +153,7 @@ __device__ void coop_backward(const R* Xc, const ParamRef<R>& prm, int T, R* Kb,
         b_g[r] = false; b_add[r] = false; b_const[r] = true;
         b_cbase[r] = R(0); b_cmul[r] = R(0); b_xcol[r] = -1;
         b_gai[r] = b_gas[r] = b_gaj[r] = b_gbi[r] = b_gbs[r] = b_gbj[r] = L::ONE;
-        b_o0[r] = b_o1[r] = L::ONE; b_kind[r] = CK_PLAIN; b_dst[r] = L::QX;
+        b_o0[r] = b_o1[r] = L::ONE; b_kind[r] = CK_PLAIN; b_dst[r] = L::DUMMY;
         if (e < NP) {                                             // Qss(i, j), i <= j
             int i, j;
             coop_pair(e, NS, i, j);
@@ -179,89 +201,120 @@ __device__ void coop_backward(const R* Xc, const ParamRef<R>& prm, int T, R* Kb,
     const bool c_ok = lane < N5;
     if (c_ok) coop_pair(lane, NQ, c_i, c_j);
     const int c_base = L::QX + c_i * NQ + c_j;
-    const int c_dst1 = (c_j < NS) ? L::V + c_i * NS + c_j : L::VS + c_i;
-    const int c_dst2 = (c_j < NS) ? L::V + c_j * NS + c_i : c_dst1;
     const int vy_y = lane - N5;                                   // lanes N5, N5+1 update vy, vyy
     const bool vy_ok = vy_y >= 0 && vy_y < 2;
-    const int st_a = lane / NQ, st_j = lane % NQ;                 // lanes < M*NQ store K / k
+    // where this lane's stage-5 results go: V(i,j) and its mirror / v(i); vy and vyy; nothing (dummy)
+    const int c_dst1 = c_ok ? ((c_j < NS) ? L::V + c_i * NS + c_j : L::VS + c_i) : (vy_ok ? L::VY + vy_y : L::DUMMY);
+    const int c_dst2 = c_ok ? ((c_j < NS) ? L::V + c_j * NS + c_i : c_dst1) : (vy_ok ? L::VYY + vy_y : L::DUMMY);
+    // lanes < M*NQ store one entry of K / k per step; the others repeat lane 0's store (same value)
     const bool st_ok = lane < M * NQ;
-    const int lu_r = lane < NQ ? lane : NQ - 1;                   // right-hand-side column of this lane
-    const bool gc_ok = lane >= NQ && lane < NQ + 2 * J;           // lanes that copy the next G row
+    const int st_a = st_ok ? lane / NQ : 0, st_j = st_ok ? lane % NQ : 0;
+    const size_t st_off = st_j < NS ? (size_t)(st_a * NS + st_j) : (size_t)st_a, st_stride = st_j < NS ? M * NS : M;
+    R* st_ptr[NT];
+    CRL_UNROLL for (int q = 0; q < NT; ++q) st_ptr[q] = (st_j < NS ? tr[q].K : tr[q].k) + st_off + (size_t)(T - 1) * st_stride;
+    // stage 3: lane (q3, r3) solves right-hand-side column r3 of trajectory q3 (and factors its Quu)
+    const bool lu_ok = lane < NT * NQ;
+    const int q3 = lu_ok ? lane / NQ : NT - 1, r3 = lu_ok ? lane % NQ : NQ - 1;
+    R* const S3 = S + q3 * L::SZ;
+    // G rows: lane (qg, g) moves entry g of trajectory qg's next row from the global table to GCUR
+    const bool gc_ok = lane < NT * 2 * J;
+    const int qg = gc_ok ? lane / (2 * J) : 0, gg = gc_ok ? lane % (2 * J) : 0;
+    const R* Gsrc = tr[0].G;
+    CRL_UNROLL for (int q = 0; q < NT; ++q)
+        if (q == qg) Gsrc = tr[q].G;
+    Gsrc += gg;
+    const int g_dst = gc_ok ? qg * L::SZ + L::GCUR + gg : L::DUMMY;
 
-    // row values needed by this lane (stage 2: x_i / u_a; stage 5: output entry and its target), one step ahead
-    R xin[R2], xin_n[R2], xv = R(0), xv_n = R(0), pv = R(0), pv_n = R(0);
-    CRL_UNROLL for (int r = 0; r < R2; ++r) {
-        xin[r] = R(0);
-        xin_n[r] = b_xcol[r] >= 0 ? Xc[(size_t)(T - 1) * D + b_xcol[r]] : R(0);
+    // row values needed by this lane (stage 2: x_i / u_a; stage 5: output entry and its target), one step ahead;
+    // lanes without such a value read column 0 and ignore it (no branches in the time loop)
+    int xcol[R2];
+    CRL_UNROLL for (int r = 0; r < R2; ++r) xcol[r] = b_xcol[r] >= 0 ? b_xcol[r] : 0;
+    const int vcol = NS + (vy_ok ? vy_y : 0), pcol = vy_ok ? vy_y : 0;
+    R xin[NT][R2], xin_n[NT][R2], xv[NT], xv_n[NT], pv[NT], pv_n[NT], g_n;
+    CRL_UNROLL for (int q = 0; q < NT; ++q) {
+        CRL_UNROLL for (int r = 0; r < R2; ++r) xin_n[q][r] = tr[q].X[(size_t)(T - 1) * D + xcol[r]];
+        xv_n[q] = tr[q].X[(size_t)(T - 1) * D + vcol];
+        pv_n[q] = tr[q].prm.get(T - 1, pcol);
     }
-    if (vy_ok) {
-        xv_n = Xc[(size_t)(T - 1) * D + NS + vy_y];
-        pv_n = prm.get(T - 1, vy_y);
-    }
-    __syncwarp();
+    g_n = Gsrc[(size_t)(T - 1) * L::GROW];                       // written above by other lanes: after the barrier
 
     for (int t = T - 1; t >= 0; --t) {
-        CRL_UNROLL for (int r = 0; r < R2; ++r) xin[r] = xin_n[r];
-        xv = xv_n;
-        pv = pv_n;
-        if (t > 0) {
-            CRL_UNROLL for (int r = 0; r < R2; ++r)
-                if (b_xcol[r] >= 0) xin_n[r] = Xc[(size_t)(t - 1) * D + b_xcol[r]];
-            if (vy_ok) {
-                xv_n = Xc[(size_t)(t - 1) * D + NS + vy_y];
-                pv_n = prm.get(t - 1, vy_y);
+        const R g_cur = g_n;
+        CRL_UNROLL for (int q = 0; q < NT; ++q) {
+            CRL_UNROLL for (int r = 0; r < R2; ++r) xin[q][r] = xin_n[q][r];
+            xv[q] = xv_n[q];
+            pv[q] = pv_n[q];
+        }
+        {
+            const int tn = t > 0 ? t - 1 : 0;
+            CRL_UNROLL for (int q = 0; q < NT; ++q) {
+                CRL_UNROLL for (int r = 0; r < R2; ++r) xin_n[q][r] = tr[q].X[(size_t)tn * D + xcol[r]];
+                xv_n[q] = tr[q].X[(size_t)tn * D + vcol];
+                pv_n[q] = tr[q].prm.get(tn, pcol);
             }
+            g_n = Gsrc[(size_t)tn * L::GROW];
         }
-        // ---- stage 1: MA = A^T V, MB = B^T V; Quu and its LU factors in every lane
-        CRL_UNROLL for (int r = 0; r < R1; ++r) {
-            const R v = coop_hsum<R>(S, a_o0[r], a_o1[r], a_kind[r], h);
-            if (a_ok[r]) S[a_dst[r]] = v;
-        }
+        // Every stage first reads all its operands, then computes, then writes: stores to the shared
+        // area would otherwise fence the loads of the next element (the compiler cannot prove that
+        // the run-time offsets do not alias) and serialise the independent chains.
+        // ---- stage 1: MA = A^T V, MB = B^T V; this step's G row; Quu of the lane's trajectory and its LU factors
+        R v1[NT][R1];
+        CRL_UNROLL for (int q = 0; q < NT; ++q)
+            CRL_UNROLL for (int r = 0; r < R1; ++r) v1[q][r] = coop_hsum<R>(S + q * L::SZ, a_o0[r], a_o1[r], a_kind[r], h);
         R Quu[M][M];
         CRL_UNROLL for (int a = 0; a < M; ++a)
             CRL_UNROLL for (int b = 0; b < M; ++b) {
-                const R acc = (S[L::V + (2 * a + 1) * NS + 2 * b + 1] * h) * h;
+                const R acc = (S3[L::V + (2 * a + 1) * NS + 2 * b + 1] * h) * h;
                 Quu[a][b] = (a == b) ? R(cost_hess<Mdl>(N + a)) + acc : acc;
             }
+        CRL_UNROLL for (int q = 0; q < NT; ++q)
+            CRL_UNROLL for (int r = 0; r < R1; ++r) S[q * L::SZ + a_dst[r]] = v1[q][r];
+        S[g_dst] = g_cur;
+        CRL_UNROLL for (int a = 0; a < M; ++a)                        // every lane of the group holds the same Quu
+            CRL_UNROLL for (int b = 0; b < M; ++b) S3[L::QUU + a * M + b] = Quu[a][b];
         LuFactors<M, R> lu;
         lu_factor<M, R>(Quu, lu);
         __syncwarp();
         // ---- stage 2: Qss, Qus, qs, qu
-        CRL_UNROLL for (int r = 0; r < R2; ++r) {
-            R acc = coop_hsum<R>(S, b_o0[r], b_o1[r], b_kind[r], h);
-            const R mga = S[b_gai[r]] * S[b_gas[r]];
-            const R mgb = S[b_gbi[r]] * S[b_gbs[r]];
-            R accg = fmadd(mga, S[b_gaj[r]], acc);
-            accg = fmadd(mgb, S[b_gbj[r]], accg);
-            acc = b_g[r] ? accg : acc;
-            const R base = b_const[r] ? b_cbase[r] : b_cmul[r] * xin[r];
-            const R out = b_add[r] ? base + acc : acc;
-            if (b_ok[r]) S[b_dst[r]] = out;
+        R o2[NT][R2];
+        CRL_UNROLL for (int q = 0; q < NT; ++q) {
+            const R* Sq = S + q * L::SZ;
+            CRL_UNROLL for (int r = 0; r < R2; ++r) {
+                R acc = coop_hsum<R>(Sq, b_o0[r], b_o1[r], b_kind[r], h);
+                const R mga = Sq[b_gai[r]] * Sq[b_gas[r]];
+                const R mgb = Sq[b_gbi[r]] * Sq[b_gbs[r]];
+                R accg = fmadd(mga, Sq[b_gaj[r]], acc);
+                accg = fmadd(mgb, Sq[b_gbj[r]], accg);
+                acc = b_g[r] ? accg : acc;
+                const R base = b_const[r] ? b_cbase[r] : b_cmul[r] * xin[q][r];
+                o2[q][r] = b_add[r] ? base + acc : acc;
+            }
         }
+        CRL_UNROLL for (int q = 0; q < NT; ++q)
+            CRL_UNROLL for (int r = 0; r < R2; ++r) S[q * L::SZ + b_dst[r]] = o2[q][r];
         __syncwarp();
-        // ---- stage 3: gains, one right-hand-side column per lane; next step's G row
+        // ---- stage 3: gains, one right-hand-side column per lane
         {
             R b[M][1];
-            CRL_UNROLL for (int a = 0; a < M; ++a) b[a][0] = S[L::QU + a * NQ + lu_r];
+            CRL_UNROLL for (int a = 0; a < M; ++a) b[a][0] = S3[L::QU + a * NQ + r3];
             lu_apply<M, 1, R>(lu, b);
-            if (lane < NQ) {
-                CRL_UNROLL for (int a = 0; a < M; ++a) S[L::KK + a * NQ + lane] = -b[a][0];
-            }
-            if (gc_ok && t > 0) S[L::GCUR + lane - NQ] = S[L::GT + (t - 1) * 2 * J + lane - NQ];
+            CRL_UNROLL for (int a = 0; a < M; ++a) S3[L::KK + a * NQ + r3] = -b[a][0];   // lanes >= NT*NQ repeat the last column
         }
         __syncwarp();
         // ---- stage 5: V, v (W = K^T Quu recomputed per element), output block, K / k to global
-        {
+        R o5[NT], kval[NT];
+        CRL_UNROLL for (int q = 0; q < NT; ++q) {
+            const R* Sq = S + q * L::SZ;
             R Ki[M], Kj[M], Ui[M], Uj[M], W[M];
             CRL_UNROLL for (int a = 0; a < M; ++a) {
-                Ki[a] = S[L::KK + a * NQ + c_i];
-                Kj[a] = S[L::KK + a * NQ + c_j];
-                Ui[a] = S[L::QU + a * NQ + c_i];
-                Uj[a] = S[L::QU + a * NQ + c_j];
+                Ki[a] = Sq[L::KK + a * NQ + c_i];
+                Kj[a] = Sq[L::KK + a * NQ + c_j];
+                Ui[a] = Sq[L::QU + a * NQ + c_i];
+                Uj[a] = Sq[L::QU + a * NQ + c_j];
             }
             CRL_UNROLL for (int b = 0; b < M; ++b) {
-                R acc = Ki[0] * Quu[0][b];
-                CRL_UNROLL for (int a = 1; a < M; ++a) acc = fmadd(Ki[a], Quu[a][b], acc);
+                R acc = Ki[0] * Sq[L::QUU + b];
+                CRL_UNROLL for (int a = 1; a < M; ++a) acc = fmadd(Ki[a], Sq[L::QUU + a * M + b], acc);
                 W[b] = acc;
             }
             R sij = Ui[0] * Kj[0], sji = Uj[0] * Ki[0], rr = W[0] * Kj[0];
@@ -270,21 +323,17 @@ __device__ void coop_backward(const R* Xc, const ParamRef<R>& prm, int T, R* Kb,
                 sji = fmadd(Uj[a], Ki[a], sji);
                 rr = fmadd(W[a], Kj[a], rr);
             }
-            const R out = ((S[c_base] + sij) + sji) + rr;
-            const R kval = S[L::KK + (st_ok ? st_a * NQ + st_j : 0)];
-            if (c_ok) {
-                S[c_dst1] = out;
-                S[c_dst2] = out;
-            }
-            if (vy_ok) {
-                const R w2 = R(2.0 * Mdl::weight(NS));
-                S[L::VY + vy_y] = (-w2) * pv + w2 * xv;
-                S[L::VYY + vy_y] = R(cost_hess<Mdl>(NS));
-            }
-            if (st_ok) {
-                if (st_j < NS) Kb[(size_t)t * (M * NS) + st_a * NS + st_j] = kval;
-                else kb[(size_t)t * M + st_a] = kval;
-            }
+            o5[q] = ((Sq[c_base] + sij) + sji) + rr;
+            kval[q] = Sq[L::KK + st_a * NQ + st_j];
+        }
+        CRL_UNROLL for (int q = 0; q < NT; ++q) {
+            R* Sq = S + q * L::SZ;
+            const R w2 = R(2.0 * Mdl::weight(NS));
+            const R vyv = (-w2) * pv[q] + w2 * xv[q];
+            Sq[c_dst1] = c_ok ? o5[q] : vyv;
+            Sq[c_dst2] = c_ok ? o5[q] : R(cost_hess<Mdl>(NS));
+            *st_ptr[q] = kval[q];
+            st_ptr[q] -= st_stride;
         }
         __syncwarp();
     }

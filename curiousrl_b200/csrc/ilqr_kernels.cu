@@ -346,11 +346,12 @@ constexpr int kCtlNext = 0;        // next unassigned trajectory of the batch
 constexpr int kCtlTail = 1;        // straggler queue: entries reserved by producers
 constexpr int kCtlHead = 2;        // straggler queue: entries claimed by finishers
 constexpr int kCtlDone = 3;        // warps that have left lane mode (and published their stragglers)
+constexpr int kCtlFin = 4;         // straggler-queue trajectories finished
 constexpr size_t kCtlBytes = 256;
 
 // Optional phase timers (development builds, -DCRL_PHASE_TIMERS): lane 0 of every warp adds the
 // SM cycles it spent per phase to control-block words kCtlTimers + phase.
-constexpr int kCtlTimers = 8;
+[[maybe_unused]] constexpr int kCtlTimers = 8;
 enum Phase : int { PH_REFILL = 0, PH_BACKWARD, PH_LINESEARCH, PH_RETIRE, PH_COOP_WAIT, PH_COOP_GATHER, PH_COOP_BACKWARD,
                    PH_COOP_LINESEARCH, PH_COOP_OUTPUT, PH_COUNT };
 #ifdef CRL_PHASE_TIMERS
@@ -389,96 +390,319 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
     return *reinterpret_cast<const volatile unsigned long long*>(p);
 }
 
-// Finishes one straggler with the whole warp: gathers its current trajectory from the producer's
-// tile column into row-major scratch, then iterates {cooperative backward pass, one-step-size-per-
-// lane line search, accept / stop} to the end and writes the results.  xfree: 32 trajectory
-// buffers [T][D]; gfree: K [T][M*NS] then k [T][M]; S: the warp's shared-memory area.
+// ------------------------------------------------------------------------------ cooperative engine
+// One warp iterates NT trajectories at a time, every lane working on every iteration
+// (ilqr_coop.cuh): the NT backward passes are stepped together (coop_backward<NT>), the line
+// search gives each trajectory GL = 32 / NT lanes, one step size per lane, every candidate
+// rollout stored in its own scratch buffer so that the accepted one simply becomes the current
+// trajectory.  Finished trajectories are replaced from a Source:
+//   BatchSource      fresh trajectories of the batch (coop_solve_kernel: the whole solve is done
+//                    this way - lowest latency per iteration, used when the batch is too small
+//                    to amortise the lane-per-trajectory kernel's long tail);
+//   StragglerSource  the straggler queue of the lane-per-trajectory kernel (its tail).
+// Scratch of one warp: xscr = NT * (GL + 1) trajectory buffers [T][D]; gscr = per trajectory
+// K [T][M*NS], k [T][M], G table [T][2J].
+
+// closed-loop rollout for one step size, stored to Xnew; returns its cost (a separate function so
+// that it gets its own register allocation)
 template <class Mdl, class R>
-__device__ void coop_finish(const SolveArgs<R>& a, const QueueEntry& ent, R* xfree, R* gfree, R* S, int lane,
-                            PhaseTimer& tm) {
-    constexpr int M = Mdl::M, D = Mdl::D, NS = Mdl::NS;
-    const int T = a.pb.T;
-    const size_t TD = (size_t)T * D;
-    R* const Kb = gfree;
-    R* const kb = gfree + (size_t)T * M * NS;
-    const long long traj = ent.traj;
-    const ParamRef<R> prm = a.pb.prm(traj);
-    double J_last = ent.J_last;
-    int it = ent.it;
-    {
-        const R* src = reinterpret_cast<const R*>(ent.src);
-        for (int e = lane; e < T * D; e += 32) xfree[e] = __ldcg(src + (size_t)e * 32);
+__device__ __noinline__ double coop_rollout(const R* X, const R* K, const R* k, R alpha, ParamRef<R> prm, Bounds<R> ub,
+                                            int T, R* Xnew) {
+    RowPrefetchFeed<Mdl, R> feed(X, K, k);
+    return rollout_closed_f<Mdl, R>(feed, alpha, prm, ub, T, View<R, Mdl::D, 1>{Xnew});
+}
+
+template <class Mdl, class R, int NT>
+__device__ __noinline__ void coop_backward_call(const CoopTraj<R> (&tr)[NT], int T, R* S, int lane) {
+    coop_backward<Mdl, R, NT>(tr, T, S, lane);
+}
+
+template <int NT>
+struct CoopGeom {
+    static constexpr int GL = (32 / NT) > 31 ? 31 : (32 / NT);   // line-search lanes (= candidates per pass) per trajectory
+    static constexpr int NBUF = GL + 1;                          // trajectory buffers per trajectory
+};
+template <class Mdl, int NT>
+__host__ __device__ constexpr long long coop_xscr_reals(int T) {
+    return (long long)NT * CoopGeom<NT>::NBUF * T * Mdl::D;
+}
+template <class Mdl>
+__host__ __device__ constexpr long long coop_gscr_reals_per_traj(int T) {
+    return (long long)T * (Mdl::M * Mdl::NS + Mdl::M + 2 * Mdl::M);
+}
+
+// Source of fresh trajectories: the batch itself.
+template <class Mdl, class R>
+struct BatchSource {
+    const SolveArgs<R>& a;
+    bool exhausted = false;
+    __device__ explicit BatchSource(const SolveArgs<R>& a_) : a(a_) {}
+    // Fills up to `want` of the empty slots (mask `empty`, bit q = slot q); slot q's trajectory is
+    // rolled out into dst[q].  Returns the mask of the slots filled; traj/it/J are set for them.
+    template <int NT>
+    __device__ unsigned take(unsigned empty, R* const (&dst)[NT], long long (&traj)[NT], int (&it)[NT], double (&J)[NT],
+                             int lane) {
+        if (exhausted || empty == 0u) return 0u;
+        const int want = __popc(empty);
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.ctl + kCtlNext, (unsigned long long)want);
+        base = __shfl_sync(kFull, base, 0);
+        if (base + want >= (unsigned long long)a.pb.B) exhausted = true;
+        unsigned got = 0u;
+        int n = 0;
+        CRL_UNROLL for (int q = 0; q < NT; ++q) {
+            if (!((empty >> q) & 1u)) continue;
+            const long long idx = (long long)base + n;
+            ++n;
+            if (idx >= a.pb.B) continue;
+            got |= 1u << q;
+            traj[q] = idx;
+            it[q] = 0;
+            J[q] = a.J_init ? a.J_init[idx] : (double)INFINITY;
+        }
+        // initial open-loop rollouts, one lane per new trajectory
+        CRL_UNROLL for (int q = 0; q < NT; ++q) {
+            if (lane == q && ((got >> q) & 1u)) {
+                const long long idx = traj[q];
+                rollout_open<Mdl, R, 1>(a.x0 + idx * Mdl::N, 1, a.u0 ? a.u0 + idx * a.u0_sb : nullptr, Mdl::M, a.pb.prm(idx),
+                                        a.pb.ub, a.pb.T, View<R, Mdl::D, 1>{dst[q]});
+            }
+        }
+        __syncwarp();
+        return got;
     }
-    __syncwarp();
-    tm.lap(PH_COOP_GATHER);
-    int curbuf = 0;
+    __device__ bool drained(int) const { return exhausted; }      // nothing more will ever come
+    __device__ void finished(int, int) {}
+};
+
+// Source of the lane kernel's tail: the straggler queue.
+template <class Mdl, class R>
+struct StragglerSource {
+    const SolveArgs<R>& a;
+    unsigned total_warps;
+    long long claim[3] = {-1, -1, -1};                            // queue index claimed for slot q, not yet published
+    __device__ StragglerSource(const SolveArgs<R>& a_, unsigned tw) : a(a_), total_warps(tw) {}
+    bool closed = false;
+    unsigned long long q_tail = 0, q_head = 0;
+    template <int NT>
+    __device__ unsigned take(unsigned empty, R* const (&dst)[NT], long long (&traj)[NT], int (&it)[NT], double (&J)[NT],
+                             int lane) {
+        static_assert(NT <= 3, "claim slots");
+        unsigned long long q_done = 0, q_fin = 0;
+        if (lane == 0) {
+            q_done = ld_volatile_u64(a.ctl + kCtlDone);
+            __threadfence();                                   // the tail is final once every warp has reported
+            q_tail = ld_volatile_u64(a.ctl + kCtlTail);
+            q_head = ld_volatile_u64(a.ctl + kCtlHead);
+            q_fin = ld_volatile_u64(a.ctl + kCtlFin);
+        }
+        q_done = __shfl_sync(kFull, q_done, 0);
+        q_tail = __shfl_sync(kFull, q_tail, 0);
+        q_head = __shfl_sync(kFull, q_head, 0);
+        q_fin = __shfl_sync(kFull, q_fin, 0);
+        closed = q_done >= (unsigned long long)total_warps;
+        // fair share of the unfinished queue trajectories per warp that serves the queue
+        const unsigned long long unfinished = q_tail > q_fin ? q_tail - q_fin : 0ull;
+        const unsigned long long servers = q_done > 0 ? q_done : 1ull;
+        unsigned long long share = (unfinished + servers - 1) / servers;
+        const int n_star = share > (unsigned long long)NT ? NT : (share < 1 ? 1 : (int)share);
+        int n_busy = NT - __popc(empty), n_clm = 0;
+        CRL_UNROLL for (int q = 0; q < NT; ++q) n_clm += claim[q] >= 0 ? 1 : 0;
+        int want = 0;
+        {
+            int free_slots = 0;
+            CRL_UNROLL for (int q = 0; q < NT; ++q) free_slots += (((empty >> q) & 1u) && claim[q] < 0) ? 1 : 0;
+            want = n_star - n_busy - n_clm;
+            if (want > free_slots) want = free_slots;
+            const unsigned long long avail = q_tail > q_head ? q_tail - q_head : 0ull;
+            if ((unsigned long long)(want > 0 ? want : 0) > avail) want = (int)avail;
+        }
+        if (want > 0) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(a.ctl + kCtlHead, (unsigned long long)want);
+            base = __shfl_sync(kFull, base, 0);
+            int n = 0;
+            CRL_UNROLL for (int q = 0; q < NT; ++q)
+                if (((empty >> q) & 1u) && claim[q] < 0 && n < want) claim[q] = (long long)base + n++;
+        }
+        unsigned got = 0u;
+        const unsigned long long qcap = (unsigned long long)total_warps * 32ull;
+        CRL_UNROLL for (int q = 0; q < NT; ++q) {
+            if (claim[q] < 0) continue;
+            int rdy = 0;
+            if (lane == 0 && (unsigned long long)claim[q] < qcap)
+                rdy = *reinterpret_cast<const volatile int*>(&a.queue[claim[q]].ready);
+            rdy = __shfl_sync(kFull, rdy, 0);
+            if (rdy == 0) {
+                if (closed && (unsigned long long)claim[q] >= q_tail) claim[q] = -1;   // the queue ended before this index
+                continue;
+            }
+            __threadfence();
+            const QueueEntry* qe = a.queue + claim[q];
+            traj[q] = __ldcg(&qe->traj);
+            const R* src = (const R*)(uintptr_t)__ldcg(reinterpret_cast<const unsigned long long*>(&qe->src));
+            J[q] = __ldcg(&qe->J_last);
+            it[q] = __ldcg(&qe->it);
+            const int n = a.pb.T * Mdl::D;
+            for (int e = lane; e < n; e += 32) dst[q][e] = __ldcg(src + (size_t)e * 32);
+            claim[q] = -1;
+            got |= 1u << q;
+        }
+        __syncwarp();
+        return got;
+    }
+    __device__ bool drained(int) const {
+        bool pending = false;
+        CRL_UNROLL for (int q = 0; q < 3; ++q) pending = pending || claim[q] >= 0;
+        return closed && !pending && q_head >= q_tail;
+    }
+    __device__ void finished(int n, int lane) {
+        if (n > 0 && lane == 0) atomicAdd(a.ctl + kCtlFin, (unsigned long long)n);
+    }
+};
+
+template <class Mdl, class R, int NT, class Source>
+__device__ void coop_engine(const SolveArgs<R>& a, Source& src, R* xscr, R* gscr, R* S, int lane, PhaseTimer& tm) {
+    constexpr int M = Mdl::M, D = Mdl::D, NS = Mdl::NS, GL = CoopGeom<NT>::GL, NBUF = CoopGeom<NT>::NBUF;
+    const int T = a.pb.T;
+    const size_t TD = (size_t)T * D, TK = (size_t)T * M * NS, Tk = (size_t)T * M;
+    const size_t TGS = (size_t)coop_gscr_reals_per_traj<Mdl>(T);
     const int tries = (a.op.ls_method == CRL_LS_NONE) ? 1 : a.op.max_ls;
     const bool feas = a.op.ls_method == CRL_LS_FEASIBILITY;
+    // slot state, identical in every lane
+    long long s_traj[NT];
+    int s_it[NT], s_cur[NT];
+    double s_J[NT];
+    CRL_UNROLL for (int q = 0; q < NT; ++q) { s_traj[q] = -1; s_it[q] = 0; s_cur[q] = 0; s_J[q] = 0.0; }
+    // line-search role of this lane: candidate lq of trajectory q_ls
+    const bool ls_lane = lane < NT * GL;
+    const int q_ls = ls_lane ? lane / GL : 0, c_ls = ls_lane ? lane % GL : 0;
+
     while (true) {
-        const R* Xc = xfree + curbuf * TD;
-        coop_backward<Mdl, R>(Xc, prm, T, Kb, kb, S, lane);
+        // ---- refill empty slots
+        unsigned empty = 0u;
+        CRL_UNROLL for (int q = 0; q < NT; ++q) empty |= (s_traj[q] < 0 ? 1u : 0u) << q;
+        if (empty != 0u) {
+            R* dst[NT];
+            CRL_UNROLL for (int q = 0; q < NT; ++q) dst[q] = xscr + (size_t)(q * NBUF) * TD;
+            const unsigned got = src.template take<NT>(empty, dst, s_traj, s_it, s_J, lane);
+            CRL_UNROLL for (int q = 0; q < NT; ++q)
+                if ((got >> q) & 1u) s_cur[q] = 0;
+            empty &= ~got;
+        }
+        tm.lap(PH_COOP_WAIT);
+        if (empty == (1u << NT) - 1u) {
+            if (src.drained(lane)) return;
+            __nanosleep(1000);
+            continue;
+        }
+        // ---- backward passes of all slots, stepped together
+        CoopTraj<R> tr[NT];
+        CRL_UNROLL for (int q = 0; q < NT; ++q) {
+            const bool on = s_traj[q] >= 0;
+            R* g = gscr + (size_t)q * TGS;
+            tr[q].X = xscr + (size_t)(q * NBUF + s_cur[q]) * TD;
+            tr[q].prm = a.pb.prm(on ? s_traj[q] : 0);
+            tr[q].K = g;
+            tr[q].k = g + TK;
+            tr[q].G = g + TK + Tk;
+            tr[q].on = on;
+        }
+        coop_backward_call<Mdl, R, NT>(tr, T, S, lane);
         __syncwarp();
         tm.lap(PH_COOP_BACKWARD);
-        bool accepted = false;
-        double J_new = J_last;
-        int taken = -1, newbuf = curbuf;
-        for (int a0 = 0; a0 < tries && !accepted; a0 += 31) {
-            const int idx = a0 + lane;
-            const bool work = lane < 31 && idx < tries;
+        // ---- line search: GL step sizes per trajectory and pass
+        bool accepted[NT];
+        int next[NT], taken[NT], newcur[NT];
+        double J_new[NT];
+        CRL_UNROLL for (int q = 0; q < NT; ++q) {
+            accepted[q] = false; next[q] = 0; taken[q] = -1; newcur[q] = s_cur[q]; J_new[q] = s_J[q];
+        }
+        while (true) {
+            bool any = false;
+            CRL_UNROLL for (int q = 0; q < NT; ++q) any = any || (s_traj[q] >= 0 && !accepted[q] && next[q] < tries);
+            if (!any) break;
+            // this lane's candidate
+            int my_next = 0, my_cur = 0;
+            bool my_pend = false;
+            double my_Jl = 0.0;
+            CoopTraj<R> mt = tr[0];
+            CRL_UNROLL for (int q = 0; q < NT; ++q)
+                if (q == q_ls) {
+                    my_next = next[q]; my_cur = s_cur[q]; my_Jl = s_J[q]; mt = tr[q];
+                    my_pend = s_traj[q] >= 0 && !accepted[q] && next[q] < tries;
+                }
+            const int idx = my_next + c_ls;
             double Jt = 0.0;
             bool ok = false;
-            if (work) {
+            if (ls_lane && my_pend && idx < tries) {
                 double al = 1.0;
                 for (int i = 0; i < idx; ++i) al = al * a.op.gamma;
-                const int buf = lane < curbuf ? lane : lane + 1;
-                RowPrefetchFeed<Mdl, R> feed(Xc, Kb, kb);
-                const View<R, D, 1> Xn{xfree + buf * TD};
-                Jt = rollout_closed_f<Mdl, R>(feed, (R)al, prm, a.pb.ub, T, Xn);
-                ok = (a.op.ls_method == CRL_LS_NONE) || ls_accept(Jt, J_last, feas);
+                const int buf = c_ls < my_cur ? c_ls : c_ls + 1;
+                Jt = coop_rollout<Mdl, R>(mt.X, mt.K, mt.k, (R)al, mt.prm, a.pb.ub, T, xscr + (size_t)(q_ls * NBUF + buf) * TD);
+                ok = (a.op.ls_method == CRL_LS_NONE) || ls_accept(Jt, my_Jl, feas);
             }
             const unsigned okm = __ballot_sync(kFull, ok);
-            if (okm != 0u) {
-                const int w = __ffs(okm) - 1;                    // lowest lane = largest step size
-                accepted = true;
-                taken = a0 + w;
-                J_new = __shfl_sync(kFull, Jt, w);
-                newbuf = w < curbuf ? w : w + 1;
+            CRL_UNROLL for (int q = 0; q < NT; ++q) {
+                const bool pend = s_traj[q] >= 0 && !accepted[q] && next[q] < tries;
+                const unsigned gm = (okm >> (q * GL)) & ((1u << GL) - 1u);
+                const int w = gm != 0u ? __ffs(gm) - 1 : 0;      // lowest lane of the group = largest step size
+                const double Jw = __shfl_sync(kFull, Jt, q * GL + w);
+                if (pend) {
+                    if (gm != 0u) {
+                        accepted[q] = true;
+                        taken[q] = next[q] + w;
+                        J_new[q] = Jw;
+                        newcur[q] = w < s_cur[q] ? w : w + 1;
+                    } else {
+                        next[q] += GL;
+                    }
+                }
             }
         }
         __syncwarp();
         tm.lap(PH_COOP_LINESEARCH);
-        const bool stop = stop_test(J_new, J_last, a.op.criterion, a.op.stop_method == CRL_STOP_RELATIVE);
-        J_last = J_new;
-        if (lane == 0) {
-            if (a.J_trace) a.J_trace[traj * a.op.max_iter + it] = J_new;
-            if (a.alpha_trace) a.alpha_trace[traj * a.op.max_iter + it] = (int8_t)taken;
-        }
-        ++it;
-        curbuf = newbuf;
-        if ((stop && a.op.check_stop) || it >= a.op.max_iter) {
+        // ---- stop test, bookkeeping, results
+        int n_fin = 0;
+        CRL_UNROLL for (int q = 0; q < NT; ++q) {
+            if (s_traj[q] < 0) continue;
+            const bool stop = stop_test(J_new[q], s_J[q], a.op.criterion, a.op.stop_method == CRL_STOP_RELATIVE);
+            s_J[q] = J_new[q];
+            s_cur[q] = newcur[q];
             if (lane == 0) {
-                a.J_out[traj] = J_last;
-                a.iters_out[traj] = it;
-                a.conv_out[traj] = (stop && a.op.check_stop) ? 1 : 0;
+                if (a.J_trace) a.J_trace[s_traj[q] * a.op.max_iter + s_it[q]] = J_new[q];
+                if (a.alpha_trace) a.alpha_trace[s_traj[q] * a.op.max_iter + s_it[q]] = (int8_t)taken[q];
             }
-            if (a.X_out) {
-                const R* src = xfree + curbuf * TD;
-                R* dst = a.X_out + traj * TD;
-                for (int e = lane; e < T * D; e += 32) dst[e] = src[e];
+            ++s_it[q];
+            if ((stop && a.op.check_stop) || s_it[q] >= a.op.max_iter) {
+                if (lane == 0) {
+                    a.J_out[s_traj[q]] = s_J[q];
+                    a.iters_out[s_traj[q]] = s_it[q];
+                    a.conv_out[s_traj[q]] = (stop && a.op.check_stop) ? 1 : 0;
+                }
+                if (a.X_out) {
+                    const R* from = xscr + (size_t)(q * NBUF + s_cur[q]) * TD;
+                    R* to = a.X_out + s_traj[q] * TD;
+                    for (int e = lane; e < T * D; e += 32) to[e] = from[e];
+                    __syncwarp();                               // the buffer is reused by the slot's next trajectory
+                    if (s_cur[q] != 0) {
+                        // (nothing to move: the next trajectory is written to buffer 0 of the slot)
+                    }
+                }
+                s_traj[q] = -1;
+                ++n_fin;
             }
-            tm.lap(PH_COOP_OUTPUT);
-            return;
         }
+        src.finished(n_fin, lane);
+        tm.lap(PH_COOP_OUTPUT);
     }
 }
 
-// Tail of the solve kernel, entered by every warp exactly once when it leaves lane mode: publishes
-// the warp's live trajectories (mask `live`; each lane's current trajectory is column `lane` of
-// `Xcol0`) on the straggler queue, then serves the queue until every warp of the grid has left
-// lane mode and the queue is empty.
-template <class Mdl, class R>
-__device__ void coop_tail(const SolveArgs<R>& a, bool live, long long traj, int it, double J_last, const R* my_col,
-                          R* xfree, R* gfree, R* S, unsigned total_warps, int lane, PhaseTimer& tm) {
+// Publishes the live trajectories of a warp that leaves lane mode on the straggler queue (mask
+// `live`; each lane's current trajectory is its column `my_col` of a tile) and reports the warp.
+template <class R>
+__device__ void publish_stragglers(const SolveArgs<R>& a, bool live, long long traj, int it, double J_last, const R* my_col,
+                                   int lane) {
     const unsigned live_mask = __ballot_sync(kFull, live);
     if (live_mask != 0u) {
         unsigned long long base = 0;
@@ -499,38 +723,29 @@ __device__ void coop_tail(const SolveArgs<R>& a, bool live, long long traj, int 
         __threadfence();
         atomicAdd(a.ctl + kCtlDone, 1ull);
     }
-    tm.lap(PH_RETIRE);
-    while (true) {
-        unsigned long long idx = 0;
-        int got = 0;
-        if (lane == 0) {
-            idx = atomicAdd(a.ctl + kCtlHead, 1ull);
-            const volatile int* rdy = &a.queue[idx].ready;
-            const bool in_range = idx < (unsigned long long)total_warps * 32ull;
-            while (true) {
-                if (in_range && *rdy != 0) { got = 1; break; }
-                if (ld_volatile_u64(a.ctl + kCtlDone) >= (unsigned long long)total_warps) {
-                    __threadfence();
-                    if (in_range && *rdy != 0) got = 1;       // published before its producer reported done
-                    break;
-                }
-                __nanosleep(1000);
-            }
-            __threadfence();
-        }
-        got = __shfl_sync(kFull, got, 0);
-        tm.lap(PH_COOP_WAIT);
-        if (!got) return;
-        idx = __shfl_sync(kFull, idx, 0);
-        QueueEntry ent;
-        const QueueEntry* qe = a.queue + idx;
-        ent.traj = __ldcg(&qe->traj);
-        ent.src = (const void*)(uintptr_t)__ldcg(reinterpret_cast<const unsigned long long*>(&qe->src));
-        ent.J_last = __ldcg(&qe->J_last);
-        ent.it = __ldcg(&qe->it);
-        coop_finish<Mdl, R>(a, ent, xfree, gfree, S, lane, tm);
-        __syncwarp();
-    }
+}
+
+#ifndef CRL_COOP_NT
+#define CRL_COOP_NT 2
+#endif
+constexpr int kCoopNT = CRL_COOP_NT;         // trajectories a warp iterates together in the cooperative engine
+
+// The whole solve by the cooperative engine: persistent grid, WARPS warps per CTA, every warp
+// takes kCoopNT trajectories of the batch at a time.
+template <class Mdl, class R, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) coop_solve_kernel(SolveArgs<R> a) {
+    using L = CoopLayout<Mdl>;
+    extern __shared__ __align__(16) unsigned char coop_smem[];
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    R* const S = reinterpret_cast<R*>(coop_smem) + (size_t)(threadIdx.x >> 5) * (kCoopNT * L::SZ);
+    R* const slot = a.ws + warp * a.slot_elems;
+    R* const xscr = slot;
+    R* const gscr = slot + coop_xscr_reals<Mdl, kCoopNT>(a.pb.T);
+    PhaseTimer tm;
+    BatchSource<Mdl, R> src(a);
+    coop_engine<Mdl, R, kCoopNT>(a, src, xscr, gscr, S, lane, tm);
+    tm.flush(a.ctl, lane);
 }
 
 // WARPS = warps per CTA, MINB = resident CTAs per SM to compile for.  SYNC = true phase-locks the
@@ -801,9 +1016,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) solve_kernel(SolveArgs<R> a)
         // Every warp reports to the straggler queue exactly once (with its live trajectories, which
         // sit in tile `cur`) and then serves it; the other X tile and the gain tiles are its scratch.
         const View<R, D, 32> Xc = cur ? Xbuf1 : Xbuf0;
-        R* const xfree = (cur ? Xbuf0 : Xbuf1).base - lane;
-        R* const gfree = Kv.base - lane;
-        coop_tail<Mdl, R>(a, traj >= 0, traj, it, J_last, Xc.base, xfree, gfree, stage_sm, gridDim.x * WARPS, lane, tm);
+        static_assert(coop_xscr_reals<Mdl, kCoopNT>(1) + kCoopNT * coop_gscr_reals_per_traj<Mdl>(1) <= 32 * (M * NS + M),
+                      "the cooperative engine's scratch must fit the gain tiles of a warp slot");
+        R* const xfree = Kv.base - lane;                               // the gain tiles are free from here on
+        R* const gfree = xfree + coop_xscr_reals<Mdl, kCoopNT>(T);
+        publish_stragglers<R>(a, traj >= 0, traj, it, J_last, Xc.base, lane);
+        tm.lap(PH_RETIRE);
+        StragglerSource<Mdl, R> src(a, gridDim.x * WARPS);
+        coop_engine<Mdl, R, kCoopNT>(a, src, xfree, gfree, stage_sm, lane, tm);
       }
     }
     tm.flush(a.ctl, lane);
@@ -852,7 +1072,7 @@ static int check_problem(const crl_problem_t* p) {
 static int check_opts(const crl_solver_opts_t* o) {
     if (!o) return CRL_ERR_BAD_ARGUMENT;
     if (o->max_iter < 0 || o->max_line_search < 0 || o->reserved2 != 0) return CRL_ERR_BAD_ARGUMENT;
-    if (o->reserved != 0 && !(o->reserved >= 2 && o->reserved <= 4) && o->reserved != 11 && o->reserved != 12)
+    if (o->reserved != 0 && o->reserved != 2 && o->reserved != 12 && o->reserved != 20 && o->reserved != 21)
         return CRL_ERR_BAD_ARGUMENT;
     if (o->line_search_method < CRL_LS_VANILLA || o->line_search_method > CRL_LS_NONE) return CRL_ERR_BAD_ARGUMENT;
     if (o->stopping_method < CRL_STOP_RELATIVE || o->stopping_method > CRL_STOP_VANILLA) return CRL_ERR_BAD_ARGUMENT;
@@ -894,8 +1114,10 @@ static size_t queue_bytes(size_t slots) { return (slots * 32 * sizeof(QueueEntry
 template <class Mdl, class R>
 static int coop_threshold_for(const crl_solver_opts_t* o, int T) {
     if (!CoopSupport<Mdl>::value || o->coop_threshold < 0) return -1;
-    if (CoopLayout<Mdl>::reals(T) > 2 * StageLayout<Mdl, R>::STAGE) return -1;
-    const int th = o->coop_threshold == 0 ? 8 : o->coop_threshold;
+    (void)T;
+    static_assert(!CoopSupport<Mdl>::value || kCoopNT * CoopLayout<Mdl>::SZ <= 2 * StageLayout<Mdl, R>::STAGE,
+                  "the cooperative engine's shared-memory area must fit the warp's staging area");
+    const int th = o->coop_threshold == 0 ? 6 : o->coop_threshold;
     return th > 32 ? 32 : th;
 }
 
@@ -932,16 +1154,20 @@ static unsigned blocks_for(long long work) { return (unsigned)((work + kBlock - 
     } while (0)
 #endif
 
-// Launch configurations of the solve kernel.  opts->reserved selects one (0 = default):
-//   2, 3, 4 : 4 warps per CTA, that many resident CTAs per SM, warps free-running
-//   11      : 8 warps per CTA, 1 CTA per SM, warps phase-locked (SYNC)
-//   12      : 4 warps per CTA, 2 CTAs per SM, phase-locked
+// Launch configurations of the solve.  opts->reserved selects one (0 = default):
+//   2      : lane-per-trajectory kernel, 4 warps per CTA, 2 resident CTAs per SM, warps free-running
+//   12     : the same, warps of a CTA phase-locked (SYNC) - the default
+//   20, 21 : the cooperative engine as the whole solve (coop_solve_kernel), 2 / 3 resident CTAs per SM
+//            (TwoLink / ThreeLink only)
+// Every configuration produces the same results bit for bit.
 template <class R> struct SolveCfg;
 template <> struct SolveCfg<double> { static constexpr int kDefault = 12; };
-template <> struct SolveCfg<float> { static constexpr int kDefault = 4; };
+template <> struct SolveCfg<float> { static constexpr int kDefault = 12; };
 
 template <class Mdl, class R, int WARPS, int MINB, bool SYNC>
 struct SolveVariant {
+    static constexpr int kWarps = WARPS;
+    static long long slot_elems(int T) { return slot_reals<Mdl>(T); }
     static constexpr int kSmem = WARPS * StageLayout<Mdl, R>::kWarpBytes;
     static int grid(int requested) {
         if (cudaFuncSetAttribute(solve_kernel<Mdl, R, WARPS, MINB, SYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -962,31 +1188,64 @@ struct SolveVariant {
     }
 };
 
+// The cooperative engine as the whole solve (coop_solve_kernel).
+template <class Mdl, class R, int WARPS, int MINB>
+struct CoopVariant {
+    static constexpr int kWarps = WARPS;
+    static long long slot_elems(int T) {
+        return coop_xscr_reals<Mdl, kCoopNT>(T) + kCoopNT * coop_gscr_reals_per_traj<Mdl>(T);
+    }
+    static constexpr int kSmem = WARPS * kCoopNT * CoopLayout<Mdl>::SZ * (int)sizeof(R);
+    static int grid(int requested) {
+        if (cudaFuncSetAttribute(coop_solve_kernel<Mdl, R, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) !=
+            cudaSuccess)
+            return -1;
+        if (requested > 0) return requested;
+        int dev = 0, sms = 0, per_sm = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coop_solve_kernel<Mdl, R, WARPS, MINB>, WARPS * 32, kSmem) !=
+            cudaSuccess)
+            return -1;
+        if (per_sm < 1) per_sm = 1;
+        return sms * per_sm;
+    }
+    static void launch(int grid_blocks, cudaStream_t s, const SolveArgs<R>& a) {
+        coop_solve_kernel<Mdl, R, WARPS, MINB><<<grid_blocks, WARPS * 32, kSmem, s>>>(a);
+    }
+};
+
+#define CRL_COOP_VARIANT(W, B, ...)                                                \
+    if constexpr (CoopSupport<Mdl>::value) { using V = CoopVariant<Mdl, R, W, B>; __VA_ARGS__; }
+
 #ifdef CRL_DEV_FAST
 #define CRL_SOLVE_VARIANT(v, ...)                                                  \
     switch (v) {                                                                   \
+        case 2: { using V = SolveVariant<Mdl, R, 4, 2, false>; __VA_ARGS__; } break;  \
         case 12: { using V = SolveVariant<Mdl, R, 4, 2, true>; __VA_ARGS__; } break;  \
+        case 20: { CRL_COOP_VARIANT(4, 2, __VA_ARGS__) } break;                       \
+        case 21: { CRL_COOP_VARIANT(4, 3, __VA_ARGS__) } break;                       \
         default: break;                                                            \
     }
 #else
 #define CRL_SOLVE_VARIANT(v, ...)                                                  \
     switch (v) {                                                                   \
         case 2: { using V = SolveVariant<Mdl, R, 4, 2, false>; __VA_ARGS__; } break;  \
-        case 3: { using V = SolveVariant<Mdl, R, 4, 3, false>; __VA_ARGS__; } break;  \
-        case 4: { using V = SolveVariant<Mdl, R, 4, 4, false>; __VA_ARGS__; } break;  \
-        case 11: { using V = SolveVariant<Mdl, R, 8, 1, true>; __VA_ARGS__; } break;  \
         case 12: { using V = SolveVariant<Mdl, R, 4, 2, true>; __VA_ARGS__; } break;  \
+        case 20: { CRL_COOP_VARIANT(4, 2, __VA_ARGS__) } break;                       \
+        case 21: { CRL_COOP_VARIANT(4, 3, __VA_ARGS__) } break;                       \
         default: break;                                                            \
     }
 #endif
 
 // grid size and warps per CTA of the configuration `variant` (0 = default); grid < 0 on error
 template <class Mdl, class R>
-static void solve_config(int requested, int variant, int* grid, int* warps) {
+static void solve_config(int requested, int variant, int T, int* grid, int* warps, long long* slot_elems) {
     const int v = variant > 0 ? variant : SolveCfg<R>::kDefault;
     *grid = -1;
-    *warps = (v == 11) ? 8 : 4;
-    CRL_SOLVE_VARIANT(v, *grid = V::grid(requested));
+    *warps = 4;
+    *slot_elems = 0;
+    CRL_SOLVE_VARIANT(v, (*grid = V::grid(requested), *warps = V::kWarps, *slot_elems = V::slot_elems(T)));
 }
 
 template <class Mdl, class R>
@@ -1157,7 +1416,7 @@ size_t crl_solve_workspace_bytes(const crl_problem_t* prob, const crl_solver_opt
     long long reals = 0;
     int grid = 0, warps = 0;
     CRL_DISPATCH(prob->model, prob->dtype,
-                 (reals = slot_reals<Mdl>(prob->horizon), solve_config<Mdl, R>(opts->grid_blocks, opts->reserved, &grid, &warps)));
+                 (solve_config<Mdl, R>(opts->grid_blocks, opts->reserved, prob->horizon, &grid, &warps, &reals)));
     if (grid <= 0) return 0;
     const size_t elem = prob->dtype == CRL_F64 ? 8 : 4;
     const size_t slots = (size_t)grid * warps;
@@ -1183,11 +1442,12 @@ int crl_solve(const crl_problem_t* prob, const crl_solver_opts_t* opts, const vo
     if (scope.status) return scope.status;
     cudaStream_t s = (cudaStream_t)stream;
     size_t qbytes = 0;
-    {
-        int grid = 0, warps = 0;
-        CRL_DISPATCH(prob->model, prob->dtype, (solve_config<Mdl, R>(opts->grid_blocks, opts->reserved, &grid, &warps)));
-        qbytes = queue_bytes((size_t)grid * warps);
-    }
+    int grid = 0, warps = 0;
+    long long slot_elems = 0;
+    CRL_DISPATCH(prob->model, prob->dtype,
+                 (solve_config<Mdl, R>(opts->grid_blocks, opts->reserved, prob->horizon, &grid, &warps, &slot_elems)));
+    if (grid <= 0) return CRL_ERR_BAD_ARGUMENT;
+    qbytes = queue_bytes((size_t)grid * warps);
     cudaError_t e = cudaMemsetAsync(workspace, 0, kCtlBytes + qbytes, s);   // counters and the queue's ready flags
     if (e != cudaSuccess) return cuda_status(e);
     CRL_DISPATCH(prob->model, prob->dtype, {
@@ -1208,9 +1468,7 @@ int crl_solve(const crl_problem_t* prob, const crl_solver_opts_t* opts, const vo
         a.queue = (QueueEntry*)((char*)workspace + kCtlBytes);
         a.ws = (R*)((char*)workspace + kCtlBytes + qbytes);
         a.coop_threshold = coop_threshold_for<Mdl, R>(opts, prob->horizon);
-        a.slot_elems = slot_reals<Mdl>(prob->horizon);
-        int grid = 0, warps = 0;
-        solve_config<Mdl, R>(opts->grid_blocks, opts->reserved, &grid, &warps);
+        a.slot_elems = slot_elems;
         solve_launch<Mdl, R>(opts->reserved, grid, s, a);
     });
     return cuda_status(cudaGetLastError());

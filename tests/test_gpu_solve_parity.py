@@ -217,3 +217,38 @@ def test_full_size_properties():
     # matches the seeded reference statistics (median 14 iterations)
     med = float(res.iterations.double().median())
     assert 10 <= med <= 20
+
+
+@pytest.mark.parametrize("model,B,T", [("ThreeLinkPlanarManipulator", 4096, 100), ("TwoLinkPlanarManipulator", 2048, 60),
+                                       ("ThreeLinkPlanarManipulator", 5, 100)])
+def test_every_scheduling_path_gives_the_same_bits(model, B, T):
+    """Results must not depend on which path finished a trajectory: lane-per-trajectory kernel only,
+    lane kernel with the cooperative tail (default and 'everything after the queue drains'),
+    free-running CTAs, and the cooperative engine as the whole solve - all bit-identical."""
+    from curiousrl_b200.utils.synthetic import synthetic_batch
+    x0, tgt = synthetic_batch(model, B, seed=3)
+    ref = make_algo(model, T, verify=False, coop_threshold=-1).solve_batch(x0, tgt, trace=True)
+    assert int((ref.iterations > 50).sum()) > 0 or B < 100          # the batch does have a tail
+    for kw in (dict(), dict(coop_threshold=32), dict(coop_threshold=2), dict(occupancy=2), dict(occupancy=20),
+               dict(occupancy=21)):
+        res = make_algo(model, T, verify=False, **kw).solve_batch(x0, tgt, trace=True)
+        for f in ("iterations", "converged", "obj_fun_value", "trajectory", "alpha_trace"):
+            assert torch.equal(getattr(res, f), getattr(ref, f)), "%s differs with %s" % (f, kw)
+        a, b = res.obj_fun_trace, ref.obj_fun_trace
+        assert torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(torch.nan_to_num(a), torch.nan_to_num(b))
+
+
+def test_cooperative_paths_fixed_work_and_line_search_modes():
+    """Cooperative engine with is_check_stop=False (carry of rejected iterations), more step sizes than
+    lanes per trajectory (several passes), line_search_method none / feasibility, vanilla stopping."""
+    from curiousrl_b200.utils.synthetic import synthetic_batch
+    model, T = "ThreeLinkPlanarManipulator", 40
+    x0, tgt = synthetic_batch(model, 96, seed=5)
+    for kw in (dict(is_check_stop=False, max_iter=25), dict(max_line_search=40, max_iter=60),
+               dict(line_search_method="none", max_iter=15), dict(line_search_method="feasibility"),
+               dict(stopping_method="vanilla", stopping_criterion=1e-3), dict(max_line_search=0, max_iter=5)):
+        ref = make_algo(model, T, verify=False, coop_threshold=-1, **kw).solve_batch(x0, tgt, trace=True)
+        for extra in (dict(coop_threshold=32), dict(occupancy=21)):
+            res = make_algo(model, T, verify=False, **kw, **extra).solve_batch(x0, tgt, trace=True)
+            for f in ("iterations", "converged", "obj_fun_value", "trajectory", "alpha_trace"):
+                assert torch.equal(getattr(res, f), getattr(ref, f)), "%s differs with %s %s" % (f, kw, extra)

@@ -64,6 +64,22 @@ def bytes_per_traj_iter(n, m, T, s):
     return s * T * (3 * d + 2 * m * (n + 1))
 
 
+def profiled_traffic(model, dtype, batch, mode):
+    """DRAM bytes (read + write) of one solve-kernel launch from the committed `ncu --set full` capture
+    of this workload (profiles/*/traffic.json, written by profiles/summarize_ncu.py), or None."""
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*", "traffic.json"))):
+        try:
+            with open(path) as fh:
+                for rec in json.load(fh):
+                    if (rec.get("model"), rec.get("dtype"), rec.get("batch"), rec.get("mode")) == (model, dtype, batch, mode):
+                        best = rec
+        except Exception:
+            pass
+    return best
+
+
 def measured_hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -174,7 +190,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_core = args.cpu_sample or 16
+    per_core = args.cpu_sample or 64
     ref = CpuReference(args.model, args.horizon)
     iters_tot, wall_tot = 0, 0.0
     for step in range(args.warmup + args.steps):
@@ -333,15 +349,20 @@ def run_b200(args):
             "config": workload_config(args, world),
             "traj_iters_per_step": iters_all, "converged_fraction": conv_all / total_B,
             "mean_iters_per_traj": iters_all / total_B,
-            "gpu_launches": args.steps,       # one persistent solve_kernel per step (+ a 256 B memset node)
+            "gpu_launches": args.steps,       # one persistent solve_kernel per step (+ one memset node of its control block)
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3},
             "roofline": {"bound": "hbm", "kernel": "solve_kernel<%s,%s>" % (args.model, args.dtype), "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": peak_src, "algorithmic_bytes_per_traj_iter": bpi}}
+                         "peak_source": peak_src, "algorithmic_bytes_per_traj_iter": bpi,
+                         "algorithmic_bytes_per_launch": iters_local * bpi}}
+    tr = profiled_traffic(args.model, args.dtype, B, args.mode)
+    if tr is not None:
+        line["roofline"]["traffic"] = tr["dram_bytes"]
+        line["roofline"]["traffic_source"] = tr.get("source")
     if world == 1 and not args.no_cpu_baseline:
-        per_core = args.cpu_sample or 32
+        per_core = args.cpu_sample or 256           # the first 256 x cores trajectories (~15-20 s)
         try:
             ref = CpuReference(args.model, T)
             iters, wall = ref.run(per_core, seed=1234)

@@ -608,7 +608,21 @@ __device__ void coop_engine(const SolveArgs<R>& a, Source& src, R* xscr, R* gscr
             tr[q].G = g + TK + Tk;
             tr[q].on = on;
         }
-        coop_backward_call<Mdl, R, NT>(tr, T, S, lane);
+        {
+            // a warp that holds a single trajectory (the end of the tail) steps it alone: lowest latency
+            int n_on = 0, q_on = 0;
+            CRL_UNROLL for (int q = 0; q < NT; ++q)
+                if (tr[q].on) { ++n_on; q_on = q; }
+            if (NT > 1 && n_on == 1) {
+                CoopTraj<R> one[1];
+                one[0] = tr[0];
+                CRL_UNROLL for (int q = 1; q < NT; ++q)
+                    if (q == q_on) one[0] = tr[q];
+                coop_backward_call<Mdl, R, 1>(one, T, S, lane);
+            } else {
+                coop_backward_call<Mdl, R, NT>(tr, T, S, lane);
+            }
+        }
         __syncwarp();
         tm.lap(PH_COOP_BACKWARD);
         // ---- line search: GL step sizes per trajectory and pass
@@ -840,7 +854,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) solve_kernel(SolveArgs<R> a)
             TileRowFeed<Mdl, R> rows(act_mask, Xc.base - lane, stage_sm, stage_bar);
             backward_fused_f<Mdl, R, NS>(rows, prm, T, Kv, kv);
         }
+#ifndef CRL_NO_MID_BARRIER
         if (SYNC) __syncthreads();
+#endif
         tm.lap(PH_BACKWARD);
 
         // ---- line search: first improving alpha = 1, g, g^2, ...
@@ -980,16 +996,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) solve_kernel(SolveArgs<R> a)
                 a.J_out[traj] = J_last;
                 a.iters_out[traj] = it;
                 a.conv_out[traj] = (stop && a.op.check_stop) ? 1 : 0;
-                if (a.X_out) {
-                    const View<R, D, 32> src = accepted ? Xn : Xc;
-                    R* dst = a.X_out + traj * T * D;
+            }
+        }
+        if (a.X_out) {
+            // Final trajectories leave the tile through the whole warp: element e of a finished lane's
+            // column goes to X_out[traj][e], 32 consecutive elements per store (a lane writing its own
+            // 8.8 KB row by row holds the warp - and, phase-locked, the CTA - for tens of microseconds).
+            for (unsigned m = __ballot_sync(kFull, finished); m != 0u; m &= m - 1u) {
+                const int owner = __ffs(m) - 1;
+                const long long tj = __shfl_sync(kFull, traj, owner);
+                const bool acc_o = __shfl_sync(kFull, (int)accepted, owner) != 0;
+                const R* col = (acc_o ? Xn.base : Xc.base) - lane + owner;
+                R* dst = a.X_out + tj * T * D;
+                const int n = T * D;
 #pragma unroll 4
-                    for (int t = 0; t < T; ++t) {
-                        const R* row = src.row(t);
-#pragma unroll
-                        for (int i = 0; i < D; ++i) dst[(size_t)t * D + i] = src.ld(row, i);
-                    }
-                }
+                for (int e = lane; e < n; e += 32) dst[e] = col[(size_t)e * 32];
             }
         }
         // lanes that go on without an accepted step carry their trajectory into the other

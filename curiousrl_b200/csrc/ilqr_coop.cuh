@@ -73,13 +73,14 @@ __device__ __forceinline__ R coop_hsum(const R* S, int o0, int o1, int kind, R h
     return kind == CK_PLAIN ? m1 : (kind == CK_HPLUS ? p + m1 : p);
 }
 
-// One trajectory of a cooperative backward pass: its current trajectory (row-major [T][D]), cost
+// One trajectory of a cooperative backward pass: its current trajectory ([T][D], element stride xs), cost
 // parameters, outputs K [T][M*NS], k [T][M] (row-major) and a scratch table [T][2J] for the variable
 // Jacobian entries - all global.  on = false: the slot is empty; its pointers must still be valid
 // scratch (the pass runs branch-free over all NT slots and ignores what an empty one produces).
 template <class R>
 struct CoopTraj {
-    const R* X;
+    const R* X;                     // element (t, c) at X[(t * D + c) * xs]
+    int xs;                         // 1 = row-major; GL = a candidate column of the engine's line-search buffers
     ParamRef<R> prm;
     R* K;
     R* k;
@@ -107,7 +108,7 @@ __device__ void coop_backward(const CoopTraj<R> (&tr)[NT], int T, R* S, int lane
     CRL_UNROLL for (int q = 0; q < NT; ++q) {
         for (int t = lane; t < T; t += 32) {
             R xu[D], ang[J], sn[J], cs[J], G[2][NS];
-            CRL_UNROLL for (int j = 0; j < J; ++j) xu[2 * j] = tr[q].X[(size_t)t * D + 2 * j];
+            CRL_UNROLL for (int j = 0; j < J; ++j) xu[2 * j] = tr[q].X[((size_t)t * D + 2 * j) * tr[q].xs];
             Mdl::template angles<R>(xu, ang);
             sincos_batch<J, R>(ang, sn, cs);
             Mdl::template jac_trig<R>(xu, sn, cs, nullptr, nullptr, G);
@@ -232,8 +233,8 @@ __device__ void coop_backward(const CoopTraj<R> (&tr)[NT], int T, R* S, int lane
     const int vcol = NS + (vy_ok ? vy_y : 0), pcol = vy_ok ? vy_y : 0;
     R xin[NT][R2], xin_n[NT][R2], xv[NT], xv_n[NT], pv[NT], pv_n[NT], g_n;
     CRL_UNROLL for (int q = 0; q < NT; ++q) {
-        CRL_UNROLL for (int r = 0; r < R2; ++r) xin_n[q][r] = tr[q].X[(size_t)(T - 1) * D + xcol[r]];
-        xv_n[q] = tr[q].X[(size_t)(T - 1) * D + vcol];
+        CRL_UNROLL for (int r = 0; r < R2; ++r) xin_n[q][r] = tr[q].X[((size_t)(T - 1) * D + xcol[r]) * tr[q].xs];
+        xv_n[q] = tr[q].X[((size_t)(T - 1) * D + vcol) * tr[q].xs];
         pv_n[q] = tr[q].prm.get(T - 1, pcol);
     }
     g_n = Gsrc[(size_t)(T - 1) * L::GROW];                       // written above by other lanes: after the barrier
@@ -248,8 +249,8 @@ __device__ void coop_backward(const CoopTraj<R> (&tr)[NT], int T, R* S, int lane
         {
             const int tn = t > 0 ? t - 1 : 0;
             CRL_UNROLL for (int q = 0; q < NT; ++q) {
-                CRL_UNROLL for (int r = 0; r < R2; ++r) xin_n[q][r] = tr[q].X[(size_t)tn * D + xcol[r]];
-                xv_n[q] = tr[q].X[(size_t)tn * D + vcol];
+                CRL_UNROLL for (int r = 0; r < R2; ++r) xin_n[q][r] = tr[q].X[((size_t)tn * D + xcol[r]) * tr[q].xs];
+                xv_n[q] = tr[q].X[((size_t)tn * D + vcol) * tr[q].xs];
                 pv_n[q] = tr[q].prm.get(tn, pcol);
             }
             g_n = Gsrc[(size_t)tn * L::GROW];
@@ -339,10 +340,190 @@ __device__ void coop_backward(const CoopTraj<R> (&tr)[NT], int T, R* S, int lane
     }
 }
 
-// Feed of a closed-loop rollout over row-major single-trajectory arrays that loads step t+1's
-// inputs while step t computes (one warp alone on an SM partition has nothing else to hide the
-// load latency with).
+// -----------------------------------------------------------------------------------------
+// Column-group backward pass: 8 lanes = one trajectory, 4 trajectories per warp in true SIMT
+// parallel.  Lane c of a group owns COLUMN c of every matrix of the Riccati step in registers
+// (c < NS: state column; c == NS: the affine column v / qs / qu / k; the rest idle), so
+//   A^T V, B^T V                      are local,
+//   (A^T V) A, (B^T V) A              need the left neighbour's column        (shuffle up by one),
+//   Quu                               needs B^T V of the odd columns          (9 shuffles),
+//   the LU of Quu                     is factored by every lane and applied to its own column,
+//   V' = Qss + S + S^T + K^T Quu K    needs K and Qus of every column         (36 shuffles),
+//   the mirror of the symmetric V'    goes through a 3 KB shared-memory transpose.
+// About 480 instructions and ~130 shuffle / shared-memory wavefronts per time step for four
+// trajectories (the element-per-lane pass above: ~300 instructions and ~150 wavefronts per
+// trajectory), and the same per-element operation sequence as riccati_step once more.
+template <class Mdl>
+struct ColGroup {
+    static constexpr int GS = 8;                              // lanes per trajectory
+    static constexpr int NG = 4;                              // trajectories per warp
+    static constexpr int SMEM = 2 * NG * Mdl::NS * GS;        // reals: double-buffered transpose area
+    static_assert(Mdl::NS + 1 <= GS, "state columns + the affine column must fit a lane group");
+};
+
 template <class Mdl, class R>
+__device__ void colgroup_backward(const CoopTraj<R> (&tr)[4], int T, R* S, int lane) {
+    using CG = ColGroup<Mdl>;
+    constexpr int NS = Mdl::NS, M = Mdl::M, J = Mdl::M, N = Mdl::N, D = Mdl::D, GS = CG::GS, NG = CG::NG;
+    const R h = R(kH);
+    const int g = lane / GS, c = lane % GS;
+    const bool is_col = c < NS, is_aff = c == NS, c_odd = (c & 1) != 0 && is_col, c_even_col = is_col && !(c & 1);
+    const int ch = c_even_col ? c / 2 : 0;                    // index of this column's angle (even columns)
+
+    // ---- G tables of the four trajectories: lanes take time steps lane, lane + 32, ...
+    CRL_UNROLL for (int q = 0; q < NG; ++q) {
+        for (int t = lane; t < T; t += 32) {
+            R xu[D], ang[J], sn[J], cs[J], G[2][NS];
+            CRL_UNROLL for (int j = 0; j < J; ++j) xu[2 * j] = tr[q].X[((size_t)t * D + 2 * j) * tr[q].xs];
+            Mdl::template angles<R>(xu, ang);
+            sincos_batch<J, R>(ang, sn, cs);
+            Mdl::template jac_trig<R>(xu, sn, cs, nullptr, nullptr, G);
+            CRL_UNROLL for (int i = 0; i < J; ++i) {
+                tr[q].G[(size_t)t * (2 * J) + i] = G[0][2 * i];
+                tr[q].G[(size_t)t * (2 * J) + J + i] = G[1][2 * i];
+            }
+        }
+    }
+    __syncwarp();
+
+    // this lane's trajectory
+    CoopTraj<R> me = tr[0];
+    CRL_UNROLL for (int q = 1; q < NG; ++q)
+        if (q == g) me = tr[q];
+    // where this lane's gains go: K[a][c] (state column) or k[a] (affine column)
+    const int kc = is_col ? c : 0;
+    R* kst = (is_aff ? me.k : me.K + kc) + (size_t)(T - 1) * (is_aff ? M : M * NS);
+    const int kst_a = is_aff ? 1 : NS, kst_t = is_aff ? M : M * NS;
+
+    // value function: column c of V (affine lane: v); output block in every lane
+    R Vc[NS], vy[2], vyy[2];
+    CRL_UNROLL for (int i = 0; i < NS; ++i) Vc[i] = R(0);
+    vy[0] = vy[1] = vyy[0] = vyy[1] = R(0);
+
+    // row values, one step ahead: G row (2J), x_i of the odd rows (J), u (M), output entries (2), targets (2)
+    R Gn[2 * J], xo_n[J], u_n[M], y_n[2], p_n[2];
+    {
+        const size_t r = (size_t)(T - 1);
+        const size_t xs = (size_t)me.xs;
+        CRL_UNROLL for (int i = 0; i < 2 * J; ++i) Gn[i] = me.G[r * (2 * J) + i];
+        CRL_UNROLL for (int j = 0; j < J; ++j) xo_n[j] = me.X[(r * D + 2 * j + 1) * xs];
+        CRL_UNROLL for (int a = 0; a < M; ++a) u_n[a] = me.X[(r * D + N + a) * xs];
+        CRL_UNROLL for (int y = 0; y < 2; ++y) { y_n[y] = me.X[(r * D + NS + y) * xs]; p_n[y] = me.prm.get(T - 1, y); }
+    }
+
+    for (int t = T - 1; t >= 0; --t) {
+        R G[2][J], xo[J], u[M], yv[2], pv[2];
+        CRL_UNROLL for (int i = 0; i < J; ++i) { G[0][i] = Gn[i]; G[1][i] = Gn[J + i]; }
+        CRL_UNROLL for (int j = 0; j < J; ++j) xo[j] = xo_n[j];
+        CRL_UNROLL for (int a = 0; a < M; ++a) u[a] = u_n[a];
+        CRL_UNROLL for (int y = 0; y < 2; ++y) { yv[y] = y_n[y]; pv[y] = p_n[y]; }
+        {
+            const size_t r = (size_t)(t > 0 ? t - 1 : 0);
+            const size_t xs = (size_t)me.xs;
+            CRL_UNROLL for (int i = 0; i < 2 * J; ++i) Gn[i] = me.G[r * (2 * J) + i];
+            CRL_UNROLL for (int j = 0; j < J; ++j) xo_n[j] = me.X[(r * D + 2 * j + 1) * xs];
+            CRL_UNROLL for (int a = 0; a < M; ++a) u_n[a] = me.X[(r * D + N + a) * xs];
+            CRL_UNROLL for (int y = 0; y < 2; ++y) { y_n[y] = me.X[(r * D + NS + y) * xs]; p_n[y] = me.prm.get((int)r, y); }
+        }
+        // ---- column c of A^T V and B^T V (affine lane: A^T v, B^T v)
+        R MA[NS], MB[M];
+        CRL_UNROLL for (int i = 0; i < NS; ++i) MA[i] = (i & 1) ? Vc[i - 1] * h + Vc[i] : Vc[i];
+        CRL_UNROLL for (int a = 0; a < M; ++a) MB[a] = Vc[2 * a + 1] * h;
+        // ---- Quu from the odd columns, factored by every lane
+        R Quu[M][M];
+        CRL_UNROLL for (int a = 0; a < M; ++a)
+            CRL_UNROLL for (int b = 0; b < M; ++b) {
+                const R acc = __shfl_sync(0xffffffffu, MB[a], 2 * b + 1, GS) * h;
+                Quu[a][b] = (a == b) ? R(cost_hess<Mdl>(N + a)) + acc : acc;
+            }
+        LuFactors<M, R> lu;
+        lu_factor<M, R>(Quu, lu);
+        // ---- column c of [Qss | qs] and [Qus | qu]
+        R Gc[2];                                              // G[y][c/2] of an even state column
+        CRL_UNROLL for (int y = 0; y < 2; ++y) {
+            Gc[y] = G[y][0];
+            CRL_UNROLL for (int i = 1; i < J; ++i) Gc[y] = (ch == i) ? G[y][i] : Gc[y];
+        }
+        R Qx[NS], Qu[M][1];
+        CRL_UNROLL for (int i = 0; i < NS; ++i) {
+            const R left = __shfl_up_sync(0xffffffffu, MA[i], 1, GS);
+            // state column: (MA[i][c-1] h + MA[i][c]) + G terms (+ Hessian on the diagonal)
+            R acc = c_odd ? left * h + MA[i] : MA[i];
+            // affine column: MA_v[i] + vy G terms, + cost gradient
+            R aff = MA[i];
+            if (!(i & 1)) {
+                R ag = fmadd(G[0][i / 2] * vyy[0], Gc[0], acc);
+                ag = fmadd(G[1][i / 2] * vyy[1], Gc[1], ag);
+                acc = c_even_col ? ag : acc;
+                aff = fmadd(vy[0], G[0][i / 2], aff);
+                aff = fmadd(vy[1], G[1][i / 2], aff);
+            }
+            const R hess = (i & 1) ? R(cost_hess<Mdl>(1)) : R(cost_hess<Mdl>(0));
+            const R diag = hess + acc;
+            const R grad = (i & 1) ? R(2.0 * Mdl::weight(1)) * xo[i / 2] : R(0.0);
+            Qx[i] = is_aff ? grad + aff : ((i == c) ? diag : acc);
+        }
+        CRL_UNROLL for (int a = 0; a < M; ++a) {
+            const R left = __shfl_up_sync(0xffffffffu, MB[a], 1, GS);
+            const R col = c_odd ? left * h + MB[a] : MB[a];
+            const R aff = R(2.0 * Mdl::weight(N)) * u[a] + MB[a];
+            Qu[a][0] = is_aff ? aff : col;
+        }
+        // ---- gains of this column
+        R Kc[M][1];
+        CRL_UNROLL for (int a = 0; a < M; ++a) Kc[a][0] = Qu[a][0];
+        lu_apply<M, 1, R>(lu, Kc);
+        CRL_UNROLL for (int a = 0; a < M; ++a) Kc[a][0] = -Kc[a][0];
+        if (is_col || is_aff) {
+            CRL_UNROLL for (int a = 0; a < M; ++a) kst[a * kst_a] = Kc[a][0];
+        }
+        kst -= kst_t;
+        // ---- new column: rows i <= c of V (affine lane: all of v)
+        R Vn[NS];
+        CRL_UNROLL for (int i = 0; i < NS; ++i) {
+            R Ki[M], Ui[M], W[M];
+            CRL_UNROLL for (int a = 0; a < M; ++a) {
+                Ki[a] = __shfl_sync(0xffffffffu, Kc[a][0], i, GS);
+                Ui[a] = __shfl_sync(0xffffffffu, Qu[a][0], i, GS);
+            }
+            CRL_UNROLL for (int b = 0; b < M; ++b) {
+                R acc = Ki[0] * Quu[0][b];
+                CRL_UNROLL for (int a = 1; a < M; ++a) acc = fmadd(Ki[a], Quu[a][b], acc);
+                W[b] = acc;
+            }
+            R sij = Ui[0] * Kc[0][0], sji = Qu[0][0] * Ki[0], rr = W[0] * Kc[0][0];
+            CRL_UNROLL for (int a = 1; a < M; ++a) {
+                sij = fmadd(Ui[a], Kc[a][0], sij);
+                sji = fmadd(Qu[a][0], Ki[a], sji);
+                rr = fmadd(W[a], Kc[a][0], rr);
+            }
+            Vn[i] = ((Qx[i] + sij) + sji) + rr;
+        }
+        // ---- mirror: V(i, c) for i > c is column i's row c
+        R* Sb = S + (t & 1) * (NG * NS * GS) + g * (NS * GS);
+        CRL_UNROLL for (int i = 0; i < NS; ++i) Sb[i * GS + c] = Vn[i];
+        __syncwarp();
+        CRL_UNROLL for (int i = 0; i < NS; ++i) {
+            const R low = Sb[(is_col ? c : 0) * GS + i];
+            Vc[i] = (is_col && i > c) ? low : Vn[i];
+        }
+        if (!is_col && !is_aff) {
+            CRL_UNROLL for (int i = 0; i < NS; ++i) Vc[i] = R(0);      // idle lanes stay at zero
+        }
+        // ---- output block
+        CRL_UNROLL for (int y = 0; y < 2; ++y) {
+            const R w2 = R(2.0 * Mdl::weight(NS));
+            vy[y] = (-w2) * pv[y] + w2 * yv[y];
+            vyy[y] = R(cost_hess<Mdl>(NS));
+        }
+    }
+    __syncwarp();
+}
+
+// Feed of a closed-loop rollout over single-trajectory arrays (old trajectory with element stride
+// XS, gains row-major) that loads step t+1's inputs while step t computes (one warp alone on an SM
+// partition has nothing else to hide the load latency with).
+template <class Mdl, class R, int XS>
 struct RowPrefetchFeed {
     static constexpr int kKN = Mdl::NS;
     const R* X;
@@ -352,11 +533,11 @@ struct RowPrefetchFeed {
     R nx[Mdl::NS], nu[Mdl::M], nK[Mdl::M * Mdl::NS], nk[Mdl::M];
     __device__ RowPrefetchFeed(const R* X_, const R* K_, const R* k_) : X(X_), K(K_), k(k_), nsteps(0) {}
     __device__ __forceinline__ void load(int t) {
-        const R* xr = X + (size_t)t * Mdl::D;
+        const R* xr = X + (size_t)t * (Mdl::D * XS);
         const R* Kr = K + (size_t)t * (Mdl::M * Mdl::NS);
         const R* kr = k + (size_t)t * Mdl::M;
-        CRL_UNROLL for (int j = 0; j < Mdl::NS; ++j) nx[j] = xr[j];
-        CRL_UNROLL for (int a = 0; a < Mdl::M; ++a) nu[a] = xr[Mdl::N + a];
+        CRL_UNROLL for (int j = 0; j < Mdl::NS; ++j) nx[j] = xr[j * XS];
+        CRL_UNROLL for (int a = 0; a < Mdl::M; ++a) nu[a] = xr[(Mdl::N + a) * XS];
         CRL_UNROLL for (int j = 0; j < Mdl::M * Mdl::NS; ++j) nK[j] = Kr[j];
         CRL_UNROLL for (int a = 0; a < Mdl::M; ++a) nk[a] = kr[a];
     }
@@ -366,7 +547,7 @@ struct RowPrefetchFeed {
     }
     __device__ void end() {}
     __device__ void row0(R* xu) const {
-        CRL_UNROLL for (int i = 0; i < Mdl::D; ++i) xu[i] = X[i];
+        CRL_UNROLL for (int i = 0; i < Mdl::D; ++i) xu[i] = X[i * XS];
     }
     __device__ void get(int t, R* xo, R* uo, R* Kc, R* kc) {
         CRL_UNROLL for (int j = 0; j < Mdl::NS; ++j) xo[j] = nx[j];

@@ -382,7 +382,7 @@ struct PhaseTimer {
 #endif
 
 template <class Mdl>
-__host__ __device__ constexpr long long slot_reals(int T) {
+__host__ __device__ constexpr long long lane_tiles_reals(int T) {
     return (long long)T * 32 * (2 * Mdl::D + Mdl::M * Mdl::NS + Mdl::M);
 }
 
@@ -400,35 +400,61 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
 //                    this way - lowest latency per iteration, used when the batch is too small
 //                    to amortise the lane-per-trajectory kernel's long tail);
 //   StragglerSource  the straggler queue of the lane-per-trajectory kernel (its tail).
-// Scratch of one warp: xscr = NT * (GL + 1) trajectory buffers [T][D]; gscr = per trajectory
-// K [T][M*NS], k [T][M], G table [T][2J].
+// Scratch of one warp: xscr = per trajectory two line-search buffers [T][D][GL] (the GL candidates of
+// a pass side by side, so that the lanes of a trajectory store 8 * GL consecutive bytes; the current
+// trajectory is one column of one of them, element stride GL); gscr = per trajectory K [T][M*NS],
+// k [T][M], G table [T][2J].
 
-// closed-loop rollout for one step size, stored to Xnew; returns its cost (a separate function so
-// that it gets its own register allocation)
-template <class Mdl, class R>
+// closed-loop rollout for one step size from a stride-XS trajectory, stored to a stride-XS column;
+// returns its cost (a separate function so that it gets its own register allocation)
+template <class Mdl, class R, int XS>
 __device__ __noinline__ double coop_rollout(const R* X, const R* K, const R* k, R alpha, ParamRef<R> prm, Bounds<R> ub,
                                             int T, R* Xnew) {
-    RowPrefetchFeed<Mdl, R> feed(X, K, k);
-    return rollout_closed_f<Mdl, R>(feed, alpha, prm, ub, T, View<R, Mdl::D, 1>{Xnew});
+    RowPrefetchFeed<Mdl, R, XS> feed(X, K, k);
+    return rollout_closed_f<Mdl, R>(feed, alpha, prm, ub, T, View<R, Mdl::D, XS>{Xnew});
 }
 
+// NT == 4: the column-group pass (8 lanes per trajectory); otherwise the element-per-lane pass
 template <class Mdl, class R, int NT>
 __device__ __noinline__ void coop_backward_call(const CoopTraj<R> (&tr)[NT], int T, R* S, int lane) {
-    coop_backward<Mdl, R, NT>(tr, T, S, lane);
+    if constexpr (NT == ColGroup<Mdl>::NG) colgroup_backward<Mdl, R>(tr, T, S, lane);
+    else coop_backward<Mdl, R, NT>(tr, T, S, lane);
 }
+
+// shared memory (reals) one warp of the engine needs
+template <class Mdl, int NT>
+__host__ __device__ constexpr int coop_smem_reals() {
+    return NT == ColGroup<Mdl>::NG ? (ColGroup<Mdl>::SMEM > CoopLayout<Mdl>::SZ ? ColGroup<Mdl>::SMEM : CoopLayout<Mdl>::SZ)
+                                   : NT * CoopLayout<Mdl>::SZ;
+}
+
+#ifndef CRL_COOP_NT
+#define CRL_COOP_NT 4
+#endif
+constexpr int kCoopNT = CRL_COOP_NT;         // trajectories a warp iterates together in the cooperative engine
 
 template <int NT>
 struct CoopGeom {
-    static constexpr int GL = (32 / NT) > 31 ? 31 : (32 / NT);   // line-search lanes (= candidates per pass) per trajectory
-    static constexpr int NBUF = GL + 1;                          // trajectory buffers per trajectory
+    static constexpr int GL = (32 / NT) > 16 ? 16 : (32 / NT);   // line-search lanes (= candidates per pass) per trajectory
 };
 template <class Mdl, int NT>
 __host__ __device__ constexpr long long coop_xscr_reals(int T) {
-    return (long long)NT * CoopGeom<NT>::NBUF * T * Mdl::D;
+    return (long long)NT * 2 * CoopGeom<NT>::GL * T * Mdl::D;
 }
 template <class Mdl>
 __host__ __device__ constexpr long long coop_gscr_reals_per_traj(int T) {
     return (long long)T * (Mdl::M * Mdl::NS + Mdl::M + 2 * Mdl::M);
+}
+template <class Mdl, int NT>
+__host__ __device__ constexpr long long coop_scratch_reals(int T) {
+    return coop_xscr_reals<Mdl, NT>(T) + NT * coop_gscr_reals_per_traj<Mdl>(T);
+}
+
+// A warp slot of the lane kernel: its tiles, followed (models with a cooperative path) by the scratch of
+// the engine it becomes in the tail.
+template <class Mdl>
+__host__ __device__ constexpr long long slot_reals(int T) {
+    return lane_tiles_reals<Mdl>(T) + (CoopSupport<Mdl>::value ? coop_scratch_reals<Mdl, kCoopNT>(T) : 0);
 }
 
 // Source of fresh trajectories: the batch itself.
@@ -442,6 +468,7 @@ struct BatchSource {
     template <int NT>
     __device__ unsigned take(unsigned empty, R* const (&dst)[NT], long long (&traj)[NT], int (&it)[NT], double (&J)[NT],
                              int lane) {
+        constexpr int GL = CoopGeom<NT>::GL;
         if (exhausted || empty == 0u) return 0u;
         const int want = __popc(empty);
         unsigned long long base = 0;
@@ -464,8 +491,8 @@ struct BatchSource {
         CRL_UNROLL for (int q = 0; q < NT; ++q) {
             if (lane == q && ((got >> q) & 1u)) {
                 const long long idx = traj[q];
-                rollout_open<Mdl, R, 1>(a.x0 + idx * Mdl::N, 1, a.u0 ? a.u0 + idx * a.u0_sb : nullptr, Mdl::M, a.pb.prm(idx),
-                                        a.pb.ub, a.pb.T, View<R, Mdl::D, 1>{dst[q]});
+                rollout_open<Mdl, R, GL>(a.x0 + idx * Mdl::N, 1, a.u0 ? a.u0 + idx * a.u0_sb : nullptr, Mdl::M, a.pb.prm(idx),
+                                         a.pb.ub, a.pb.T, View<R, Mdl::D, GL>{dst[q]});
             }
         }
         __syncwarp();
@@ -480,14 +507,14 @@ template <class Mdl, class R>
 struct StragglerSource {
     const SolveArgs<R>& a;
     unsigned total_warps;
-    long long claim[3] = {-1, -1, -1};                            // queue index claimed for slot q, not yet published
+    long long claim[4] = {-1, -1, -1, -1};                            // queue index claimed for slot q, not yet published
     __device__ StragglerSource(const SolveArgs<R>& a_, unsigned tw) : a(a_), total_warps(tw) {}
     bool closed = false;
     unsigned long long q_tail = 0, q_head = 0;
     template <int NT>
     __device__ unsigned take(unsigned empty, R* const (&dst)[NT], long long (&traj)[NT], int (&it)[NT], double (&J)[NT],
                              int lane) {
-        static_assert(NT <= 3, "claim slots");
+        static_assert(NT <= 4, "claim slots");
         unsigned long long q_done = 0, q_fin = 0;
         if (lane == 0) {
             q_done = ld_volatile_u64(a.ctl + kCtlDone);
@@ -544,7 +571,7 @@ struct StragglerSource {
             J[q] = __ldcg(&qe->J_last);
             it[q] = __ldcg(&qe->it);
             const int n = a.pb.T * Mdl::D;
-            for (int e = lane; e < n; e += 32) dst[q][e] = __ldcg(src + (size_t)e * 32);
+            for (int e = lane; e < n; e += 32) dst[q][(size_t)e * CoopGeom<NT>::GL] = __ldcg(src + (size_t)e * 32);
             claim[q] = -1;
             got |= 1u << q;
         }
@@ -553,7 +580,7 @@ struct StragglerSource {
     }
     __device__ bool drained(int) const {
         bool pending = false;
-        CRL_UNROLL for (int q = 0; q < 3; ++q) pending = pending || claim[q] >= 0;
+        CRL_UNROLL for (int q = 0; q < 4; ++q) pending = pending || claim[q] >= 0;
         return closed && !pending && q_head >= q_tail;
     }
     __device__ void finished(int n, int lane) {
@@ -563,31 +590,32 @@ struct StragglerSource {
 
 template <class Mdl, class R, int NT, class Source>
 __device__ void coop_engine(const SolveArgs<R>& a, Source& src, R* xscr, R* gscr, R* S, int lane, PhaseTimer& tm) {
-    constexpr int M = Mdl::M, D = Mdl::D, NS = Mdl::NS, GL = CoopGeom<NT>::GL, NBUF = CoopGeom<NT>::NBUF;
+    constexpr int M = Mdl::M, D = Mdl::D, NS = Mdl::NS, GL = CoopGeom<NT>::GL;
     const int T = a.pb.T;
     const size_t TD = (size_t)T * D, TK = (size_t)T * M * NS, Tk = (size_t)T * M;
     const size_t TGS = (size_t)coop_gscr_reals_per_traj<Mdl>(T);
+    const size_t BUF = TD * GL;                               // one line-search buffer [T][D][GL]
     const int tries = (a.op.ls_method == CRL_LS_NONE) ? 1 : a.op.max_ls;
     const bool feas = a.op.ls_method == CRL_LS_FEASIBILITY;
-    // slot state, identical in every lane
+    // slot state, identical in every lane: the current trajectory of slot q is column s_col[q] of its buffer s_buf[q]
     long long s_traj[NT];
-    int s_it[NT], s_cur[NT];
+    int s_it[NT], s_buf[NT], s_col[NT];
     double s_J[NT];
-    CRL_UNROLL for (int q = 0; q < NT; ++q) { s_traj[q] = -1; s_it[q] = 0; s_cur[q] = 0; s_J[q] = 0.0; }
-    // line-search role of this lane: candidate lq of trajectory q_ls
+    CRL_UNROLL for (int q = 0; q < NT; ++q) { s_traj[q] = -1; s_it[q] = 0; s_buf[q] = 0; s_col[q] = 0; s_J[q] = 0.0; }
+    // line-search role of this lane: candidate c_ls of trajectory q_ls
     const bool ls_lane = lane < NT * GL;
     const int q_ls = ls_lane ? lane / GL : 0, c_ls = ls_lane ? lane % GL : 0;
 
     while (true) {
-        // ---- refill empty slots
+        // ---- refill empty slots (a new trajectory goes to column 0 of buffer 0 of its slot)
         unsigned empty = 0u;
         CRL_UNROLL for (int q = 0; q < NT; ++q) empty |= (s_traj[q] < 0 ? 1u : 0u) << q;
         if (empty != 0u) {
             R* dst[NT];
-            CRL_UNROLL for (int q = 0; q < NT; ++q) dst[q] = xscr + (size_t)(q * NBUF) * TD;
+            CRL_UNROLL for (int q = 0; q < NT; ++q) dst[q] = xscr + (size_t)(2 * q) * BUF;
             const unsigned got = src.template take<NT>(empty, dst, s_traj, s_it, s_J, lane);
             CRL_UNROLL for (int q = 0; q < NT; ++q)
-                if ((got >> q) & 1u) s_cur[q] = 0;
+                if ((got >> q) & 1u) { s_buf[q] = 0; s_col[q] = 0; }
             empty &= ~got;
         }
         tm.lap(PH_COOP_WAIT);
@@ -601,7 +629,8 @@ __device__ void coop_engine(const SolveArgs<R>& a, Source& src, R* xscr, R* gscr
         CRL_UNROLL for (int q = 0; q < NT; ++q) {
             const bool on = s_traj[q] >= 0;
             R* g = gscr + (size_t)q * TGS;
-            tr[q].X = xscr + (size_t)(q * NBUF + s_cur[q]) * TD;
+            tr[q].X = xscr + (size_t)(2 * q + s_buf[q]) * BUF + s_col[q];
+            tr[q].xs = GL;
             tr[q].prm = a.pb.prm(on ? s_traj[q] : 0);
             tr[q].K = g;
             tr[q].k = g + TK;
@@ -625,25 +654,25 @@ __device__ void coop_engine(const SolveArgs<R>& a, Source& src, R* xscr, R* gscr
         }
         __syncwarp();
         tm.lap(PH_COOP_BACKWARD);
-        // ---- line search: GL step sizes per trajectory and pass
+        // ---- line search: GL step sizes per trajectory and pass, candidates side by side in the slot's other buffer
         bool accepted[NT];
-        int next[NT], taken[NT], newcur[NT];
+        int next[NT], taken[NT], newcol[NT];
         double J_new[NT];
         CRL_UNROLL for (int q = 0; q < NT; ++q) {
-            accepted[q] = false; next[q] = 0; taken[q] = -1; newcur[q] = s_cur[q]; J_new[q] = s_J[q];
+            accepted[q] = false; next[q] = 0; taken[q] = -1; newcol[q] = 0; J_new[q] = s_J[q];
         }
         while (true) {
             bool any = false;
             CRL_UNROLL for (int q = 0; q < NT; ++q) any = any || (s_traj[q] >= 0 && !accepted[q] && next[q] < tries);
             if (!any) break;
             // this lane's candidate
-            int my_next = 0, my_cur = 0;
+            int my_next = 0, my_buf = 0;
             bool my_pend = false;
             double my_Jl = 0.0;
             CoopTraj<R> mt = tr[0];
             CRL_UNROLL for (int q = 0; q < NT; ++q)
                 if (q == q_ls) {
-                    my_next = next[q]; my_cur = s_cur[q]; my_Jl = s_J[q]; mt = tr[q];
+                    my_next = next[q]; my_buf = s_buf[q]; my_Jl = s_J[q]; mt = tr[q];
                     my_pend = s_traj[q] >= 0 && !accepted[q] && next[q] < tries;
                 }
             const int idx = my_next + c_ls;
@@ -652,8 +681,8 @@ __device__ void coop_engine(const SolveArgs<R>& a, Source& src, R* xscr, R* gscr
             if (ls_lane && my_pend && idx < tries) {
                 double al = 1.0;
                 for (int i = 0; i < idx; ++i) al = al * a.op.gamma;
-                const int buf = c_ls < my_cur ? c_ls : c_ls + 1;
-                Jt = coop_rollout<Mdl, R>(mt.X, mt.K, mt.k, (R)al, mt.prm, a.pb.ub, T, xscr + (size_t)(q_ls * NBUF + buf) * TD);
+                Jt = coop_rollout<Mdl, R, GL>(mt.X, mt.K, mt.k, (R)al, mt.prm, a.pb.ub, T,
+                                              xscr + (size_t)(2 * q_ls + (my_buf ^ 1)) * BUF + c_ls);
                 ok = (a.op.ls_method == CRL_LS_NONE) || ls_accept(Jt, my_Jl, feas);
             }
             const unsigned okm = __ballot_sync(kFull, ok);
@@ -667,7 +696,7 @@ __device__ void coop_engine(const SolveArgs<R>& a, Source& src, R* xscr, R* gscr
                         accepted[q] = true;
                         taken[q] = next[q] + w;
                         J_new[q] = Jw;
-                        newcur[q] = w < s_cur[q] ? w : w + 1;
+                        newcol[q] = w;
                     } else {
                         next[q] += GL;
                     }
@@ -682,7 +711,7 @@ __device__ void coop_engine(const SolveArgs<R>& a, Source& src, R* xscr, R* gscr
             if (s_traj[q] < 0) continue;
             const bool stop = stop_test(J_new[q], s_J[q], a.op.criterion, a.op.stop_method == CRL_STOP_RELATIVE);
             s_J[q] = J_new[q];
-            s_cur[q] = newcur[q];
+            if (accepted[q]) { s_buf[q] ^= 1; s_col[q] = newcol[q]; }
             if (lane == 0) {
                 if (a.J_trace) a.J_trace[s_traj[q] * a.op.max_iter + s_it[q]] = J_new[q];
                 if (a.alpha_trace) a.alpha_trace[s_traj[q] * a.op.max_iter + s_it[q]] = (int8_t)taken[q];
@@ -695,13 +724,10 @@ __device__ void coop_engine(const SolveArgs<R>& a, Source& src, R* xscr, R* gscr
                     a.conv_out[s_traj[q]] = (stop && a.op.check_stop) ? 1 : 0;
                 }
                 if (a.X_out) {
-                    const R* from = xscr + (size_t)(q * NBUF + s_cur[q]) * TD;
+                    const R* from = xscr + (size_t)(2 * q + s_buf[q]) * BUF + s_col[q];
                     R* to = a.X_out + s_traj[q] * TD;
-                    for (int e = lane; e < T * D; e += 32) to[e] = from[e];
-                    __syncwarp();                               // the buffer is reused by the slot's next trajectory
-                    if (s_cur[q] != 0) {
-                        // (nothing to move: the next trajectory is written to buffer 0 of the slot)
-                    }
+                    for (int e = lane; e < T * D; e += 32) to[e] = from[(size_t)e * GL];
+                    __syncwarp();                               // the buffers are reused by the slot's next trajectory
                 }
                 s_traj[q] = -1;
                 ++n_fin;
@@ -739,26 +765,21 @@ __device__ void publish_stragglers(const SolveArgs<R>& a, bool live, long long t
     }
 }
 
-#ifndef CRL_COOP_NT
-#define CRL_COOP_NT 2
-#endif
-constexpr int kCoopNT = CRL_COOP_NT;         // trajectories a warp iterates together in the cooperative engine
 
 // The whole solve by the cooperative engine: persistent grid, WARPS warps per CTA, every warp
 // takes kCoopNT trajectories of the batch at a time.
-template <class Mdl, class R, int WARPS, int MINB>
+template <class Mdl, class R, int WARPS, int MINB, int NT>
 __global__ void __launch_bounds__(WARPS * 32, MINB) coop_solve_kernel(SolveArgs<R> a) {
-    using L = CoopLayout<Mdl>;
     extern __shared__ __align__(16) unsigned char coop_smem[];
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    R* const S = reinterpret_cast<R*>(coop_smem) + (size_t)(threadIdx.x >> 5) * (kCoopNT * L::SZ);
+    R* const S = reinterpret_cast<R*>(coop_smem) + (size_t)(threadIdx.x >> 5) * coop_smem_reals<Mdl, NT>();
     R* const slot = a.ws + warp * a.slot_elems;
     R* const xscr = slot;
-    R* const gscr = slot + coop_xscr_reals<Mdl, kCoopNT>(a.pb.T);
+    R* const gscr = slot + coop_xscr_reals<Mdl, NT>(a.pb.T);
     PhaseTimer tm;
     BatchSource<Mdl, R> src(a);
-    coop_engine<Mdl, R, kCoopNT>(a, src, xscr, gscr, S, lane, tm);
+    coop_engine<Mdl, R, NT>(a, src, xscr, gscr, S, lane, tm);
     tm.flush(a.ctl, lane);
 }
 
@@ -1037,9 +1058,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) solve_kernel(SolveArgs<R> a)
         // Every warp reports to the straggler queue exactly once (with its live trajectories, which
         // sit in tile `cur`) and then serves it; the other X tile and the gain tiles are its scratch.
         const View<R, D, 32> Xc = cur ? Xbuf1 : Xbuf0;
-        static_assert(coop_xscr_reals<Mdl, kCoopNT>(1) + kCoopNT * coop_gscr_reals_per_traj<Mdl>(1) <= 32 * (M * NS + M),
-                      "the cooperative engine's scratch must fit the gain tiles of a warp slot");
-        R* const xfree = Kv.base - lane;                               // the gain tiles are free from here on
+        R* const xfree = a.ws + slot * a.slot_elems + lane_tiles_reals<Mdl>(T);   // engine scratch behind the tiles
         R* const gfree = xfree + coop_xscr_reals<Mdl, kCoopNT>(T);
         publish_stragglers<R>(a, traj >= 0, traj, it, J_last, Xc.base, lane);
         tm.lap(PH_RETIRE);
@@ -1093,7 +1112,7 @@ static int check_problem(const crl_problem_t* p) {
 static int check_opts(const crl_solver_opts_t* o) {
     if (!o) return CRL_ERR_BAD_ARGUMENT;
     if (o->max_iter < 0 || o->max_line_search < 0 || o->reserved2 != 0) return CRL_ERR_BAD_ARGUMENT;
-    if (o->reserved != 0 && o->reserved != 2 && o->reserved != 12 && o->reserved != 20 && o->reserved != 21)
+    if (o->reserved != 0 && o->reserved != 2 && o->reserved != 12 && o->reserved != 20 && o->reserved != 21 && o->reserved != 22)
         return CRL_ERR_BAD_ARGUMENT;
     if (o->line_search_method < CRL_LS_VANILLA || o->line_search_method > CRL_LS_NONE) return CRL_ERR_BAD_ARGUMENT;
     if (o->stopping_method < CRL_STOP_RELATIVE || o->stopping_method > CRL_STOP_VANILLA) return CRL_ERR_BAD_ARGUMENT;
@@ -1136,7 +1155,7 @@ template <class Mdl, class R>
 static int coop_threshold_for(const crl_solver_opts_t* o, int T) {
     if (!CoopSupport<Mdl>::value || o->coop_threshold < 0) return -1;
     (void)T;
-    static_assert(!CoopSupport<Mdl>::value || kCoopNT * CoopLayout<Mdl>::SZ <= 2 * StageLayout<Mdl, R>::STAGE,
+    static_assert(!CoopSupport<Mdl>::value || coop_smem_reals<Mdl, kCoopNT>() <= 2 * StageLayout<Mdl, R>::STAGE,
                   "the cooperative engine's shared-memory area must fit the warp's staging area");
     const int th = o->coop_threshold == 0 ? 6 : o->coop_threshold;
     return th > 32 ? 32 : th;
@@ -1209,43 +1228,42 @@ struct SolveVariant {
     }
 };
 
-// The cooperative engine as the whole solve (coop_solve_kernel).
-template <class Mdl, class R, int WARPS, int MINB>
+// The cooperative engine as the whole solve (coop_solve_kernel), NT trajectories per warp.
+template <class Mdl, class R, int WARPS, int MINB, int NT>
 struct CoopVariant {
     static constexpr int kWarps = WARPS;
-    static long long slot_elems(int T) {
-        return coop_xscr_reals<Mdl, kCoopNT>(T) + kCoopNT * coop_gscr_reals_per_traj<Mdl>(T);
-    }
-    static constexpr int kSmem = WARPS * kCoopNT * CoopLayout<Mdl>::SZ * (int)sizeof(R);
+    static long long slot_elems(int T) { return coop_scratch_reals<Mdl, NT>(T); }
+    static constexpr int kSmem = WARPS * coop_smem_reals<Mdl, NT>() * (int)sizeof(R);
     static int grid(int requested) {
-        if (cudaFuncSetAttribute(coop_solve_kernel<Mdl, R, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) !=
-            cudaSuccess)
+        if (cudaFuncSetAttribute(coop_solve_kernel<Mdl, R, WARPS, MINB, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kSmem) != cudaSuccess)
             return -1;
         if (requested > 0) return requested;
         int dev = 0, sms = 0, per_sm = 0;
         if (cudaGetDevice(&dev) != cudaSuccess) return -1;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coop_solve_kernel<Mdl, R, WARPS, MINB>, WARPS * 32, kSmem) !=
-            cudaSuccess)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coop_solve_kernel<Mdl, R, WARPS, MINB, NT>, WARPS * 32,
+                                                          kSmem) != cudaSuccess)
             return -1;
         if (per_sm < 1) per_sm = 1;
         return sms * per_sm;
     }
     static void launch(int grid_blocks, cudaStream_t s, const SolveArgs<R>& a) {
-        coop_solve_kernel<Mdl, R, WARPS, MINB><<<grid_blocks, WARPS * 32, kSmem, s>>>(a);
+        coop_solve_kernel<Mdl, R, WARPS, MINB, NT><<<grid_blocks, WARPS * 32, kSmem, s>>>(a);
     }
 };
 
-#define CRL_COOP_VARIANT(W, B, ...)                                                \
-    if constexpr (CoopSupport<Mdl>::value) { using V = CoopVariant<Mdl, R, W, B>; __VA_ARGS__; }
+#define CRL_COOP_VARIANT(W, B, NT, ...)                                            \
+    if constexpr (CoopSupport<Mdl>::value) { using V = CoopVariant<Mdl, R, W, B, NT>; __VA_ARGS__; }
 
 #ifdef CRL_DEV_FAST
 #define CRL_SOLVE_VARIANT(v, ...)                                                  \
     switch (v) {                                                                   \
         case 2: { using V = SolveVariant<Mdl, R, 4, 2, false>; __VA_ARGS__; } break;  \
         case 12: { using V = SolveVariant<Mdl, R, 4, 2, true>; __VA_ARGS__; } break;  \
-        case 20: { CRL_COOP_VARIANT(4, 2, __VA_ARGS__) } break;                       \
-        case 21: { CRL_COOP_VARIANT(4, 3, __VA_ARGS__) } break;                       \
+        case 20: { CRL_COOP_VARIANT(4, 2, 4, __VA_ARGS__) } break;                       \
+        case 21: { CRL_COOP_VARIANT(4, 3, 4, __VA_ARGS__) } break;                       \
+        case 22: { CRL_COOP_VARIANT(4, 2, 2, __VA_ARGS__) } break;                       \
         default: break;                                                            \
     }
 #else
@@ -1253,8 +1271,8 @@ struct CoopVariant {
     switch (v) {                                                                   \
         case 2: { using V = SolveVariant<Mdl, R, 4, 2, false>; __VA_ARGS__; } break;  \
         case 12: { using V = SolveVariant<Mdl, R, 4, 2, true>; __VA_ARGS__; } break;  \
-        case 20: { CRL_COOP_VARIANT(4, 2, __VA_ARGS__) } break;                       \
-        case 21: { CRL_COOP_VARIANT(4, 3, __VA_ARGS__) } break;                       \
+        case 20: { CRL_COOP_VARIANT(4, 2, 4, __VA_ARGS__) } break;                       \
+        case 21: { CRL_COOP_VARIANT(4, 3, 4, __VA_ARGS__) } break;                       \
         default: break;                                                            \
     }
 #endif

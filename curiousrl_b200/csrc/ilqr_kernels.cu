@@ -1157,7 +1157,7 @@ static int coop_threshold_for(const crl_solver_opts_t* o, int T) {
     (void)T;
     static_assert(!CoopSupport<Mdl>::value || coop_smem_reals<Mdl, kCoopNT>() <= 2 * StageLayout<Mdl, R>::STAGE,
                   "the cooperative engine's shared-memory area must fit the warp's staging area");
-    const int th = o->coop_threshold == 0 ? 6 : o->coop_threshold;
+    const int th = o->coop_threshold == 0 ? 12 : o->coop_threshold;
     return th > 32 ? 32 : th;
 }
 
@@ -1197,8 +1197,8 @@ static unsigned blocks_for(long long work) { return (unsigned)((work + kBlock - 
 // Launch configurations of the solve.  opts->reserved selects one (0 = default):
 //   2      : lane-per-trajectory kernel, 4 warps per CTA, 2 resident CTAs per SM, warps free-running
 //   12     : the same, warps of a CTA phase-locked (SYNC) - the default
-//   20, 21 : the cooperative engine as the whole solve (coop_solve_kernel), 2 / 3 resident CTAs per SM
-//            (TwoLink / ThreeLink only)
+//   20, 21 : the cooperative engine as the whole solve (coop_solve_kernel, 4 trajectories per warp), 2 / 3
+//            resident CTAs per SM (TwoLink / ThreeLink only); 22 (development builds): 2 trajectories per warp
 // Every configuration produces the same results bit for bit.
 template <class R> struct SolveCfg;
 template <> struct SolveCfg<double> { static constexpr int kDefault = 12; };

@@ -75,7 +75,7 @@ typedef struct crl_solver_opts {
     int32_t reserved;           /* launch configuration of the solve kernel, 0 = default       */
     int32_t coop_threshold;     /* once the batch queue is empty, a warp with at most this many
                                    unfinished trajectories hands them to the warp-cooperative
-                                   engine (a few trajectories per warp): 0 = default (6), < 0 = never.
+                                   engine (four trajectories per warp): 0 = default (12), < 0 = never.
                                    Scheduling only - results do not depend on it.                */
     int32_t reserved2;          /* must be 0                                                   */
 } crl_solver_opts_t;

@@ -33,6 +33,11 @@ constexpr int kCoopMax = 6;        // a drained warp with <= this many live traj
 #define CRL_LS_CHUNK 4
 #endif
 constexpr int kLsChunk = CRL_LS_CHUNK;   // step sizes evaluated per pass of the line search
+#ifndef CRL_HELP_MAX
+#define CRL_HELP_MAX 16
+#endif
+constexpr int kHelpMax = CRL_HELP_MAX;   // after the first pass, at most this many still-searching lanes are helped by the others
+constexpr bool kHelpLs = kHelpMax > 0;
 
 template <class R>
 struct ProblemDev {
@@ -216,13 +221,17 @@ struct TileFeed {
     R* sm;                        // this warp's two stages
     unsigned long long* bar;      // this warp's two barriers
     unsigned mask;
-    int lane, leader, nsteps;
+    int lane, col, leader, nsteps;
 
-    // `mask_` = the lanes that take part, computed by the caller where the warp is still converged
-    __device__ TileFeed(unsigned mask_, const R* gX_, const R* gK_, const R* gk_, R* sm_, unsigned long long* bar_)
+    // `mask_` = the lanes that take part, computed by the caller where the warp is still converged;
+    // col_ = the tile column (trajectory) this lane reads: its own, or another lane's when it helps
+    // with that lane's line search
+    __device__ TileFeed(unsigned mask_, const R* gX_, const R* gK_, const R* gk_, R* sm_, unsigned long long* bar_,
+                        int col_ = -1)
         : gX(gX_), gK(gK_), gk(gk_), sm(sm_), bar(bar_) {
         mask = mask_;
         lane = threadIdx.x & 31;
+        col = col_ < 0 ? lane : col_;
         leader = __ffs(mask) - 1;
         nsteps = 0;
     }
@@ -248,13 +257,13 @@ struct TileFeed {
     __device__ void end() { __syncwarp(mask); }
     __device__ void row0(R* xu) const {
 #pragma unroll
-        for (int i = 0; i < Mdl::D; ++i) xu[i] = gX[i * 32 + lane];
+        for (int i = 0; i < Mdl::D; ++i) xu[i] = gX[i * 32 + col];
     }
     __device__ void get(int t, R* xo, R* uo, R* Kc, R* kc) {
         __syncwarp(mask);                                   // everyone is done with the stage about to be refilled
         if (lane == leader && t + 1 < nsteps) issue(t + 1);
         mbar_wait(bar + (t & 1), (unsigned)((t >> 1) & 1));
-        const R* s0 = sm + (t & 1) * L::STAGE + lane;
+        const R* s0 = sm + (t & 1) * L::STAGE + col;
 #pragma unroll
         for (int j = 0; j < Mdl::NS; ++j) xo[j] = s0[j * 32];
 #pragma unroll
@@ -950,6 +959,59 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) solve_kernel(SolveArgs<R> a)
                 const bool pending = active && !accepted;
                 const unsigned pend_mask = __ballot_sync(kFull, pending);
                 if (pend_mask == 0u) break;
+                const int n_pend = __popc(pend_mask);
+                if (kHelpLs && a0 > 0 && n_pend <= kHelpMax) {
+                    // Few lanes are still searching (after the first pass 80 % have their step): instead of
+                    // another multi-alpha pass of the whole warp, the 32 lanes share the pending
+                    // trajectories - G = 32 / n_pend lanes per trajectory, one step size each, costs only,
+                    // reading the owner's column of the staged tile.  The accepted step is stored by the
+                    // owner in the replay pass below.  Same arithmetic per candidate as everywhere else.
+                    const int G = 32 / n_pend;
+                    const int r = lane / G, j = lane - r * G;
+                    const bool has = r < n_pend;
+                    const int owner = has ? (int)__fns(pend_mask, 0, r + 1) : 0;
+                    const int idx = a0 + j;
+                    const bool work = has && idx < tries;
+                    const double Jl_o = __shfl_sync(kFull, J_last, owner);
+                    const unsigned long long pp = __shfl_sync(kFull, (unsigned long long)(uintptr_t)prm.ptr, owner);
+                    const ParamRef<R> prm_o{(const R*)(uintptr_t)pp, __shfl_sync(kFull, prm.stride_t, owner)};
+                    const unsigned work_mask = __ballot_sync(kFull, work);
+                    double Jt = 0.0;
+                    bool ok = false;
+                    if (work) {
+                        double al = alpha;
+                        for (int i = 0; i < j; ++i) al = al * a.op.gamma;
+                        TileFeed<Mdl, R> feed(work_mask, Xc.base - lane, Kv.base - lane, kv.base - lane, stage_sm, stage_bar, owner);
+                        const R alr[1] = {(R)al};
+                        double Jc[1];
+                        rollout_multi_f<Mdl, R, 1, TileFeed<Mdl, R>, 32, false>(feed, alr, prm_o, a.pb.ub, T, 0, Xn, Jc);
+                        Jt = Jc[0];
+                        ok = ls_accept(Jt, Jl_o, feas);
+                    }
+                    const unsigned okm = __ballot_sync(kFull, ok);
+                    int w = -1, src_lane = lane;
+                    if (pending) {
+                        const int rme = __popc(pend_mask & ((1u << lane) - 1u));
+                        const unsigned gm = (okm >> (rme * G)) & (G >= 32 ? kFull : ((1u << G) - 1u));
+                        if (gm != 0u) {
+                            w = __ffs(gm) - 1;                  // lowest lane of the group = largest step size
+                            src_lane = rme * G + w;
+                        }
+                    }
+                    const double Jw = __shfl_sync(kFull, Jt, src_lane);
+                    if (pending && w >= 0) {
+                        accepted = true;
+                        J_new = Jw;
+                        taken = a0 + w;
+                        double al = alpha;
+                        for (int i = 0; i < w; ++i) al = al * a.op.gamma;
+                        alpha_taken = al;
+                        replay = true;
+                    }
+                    for (int i = 0; i < G; ++i) alpha = alpha * a.op.gamma;
+                    a0 += G;
+                    continue;
+                }
                 // a warp whose pending lanes all expect alpha = 1 to be accepted tries it alone first
                 const bool wide = (tries - a0 >= 2) && (a0 > 0 || __any_sync(kFull, pending && pred > 0));
                 if (wide) {

@@ -16,7 +16,8 @@
 // which path finished it (tests/test_gpu_solve_parity.py::test_coop_matches_lane_mode checks
 // bit equality).
 //
-// Implemented for the kinematic chains (TwoLink, ThreeLink: constant A, B; variable G only).
+// The element-per-lane pass (coop_backward) exists for the kinematic chains (TwoLink, ThreeLink:
+// constant A, B; variable G only); the column-group passes for all three models.
 #pragma once
 
 #include "ilqr_core.cuh"
@@ -26,6 +27,7 @@ namespace crl {
 template <class Mdl> struct CoopSupport { static constexpr bool value = false; };
 template <> struct CoopSupport<TwoLink> { static constexpr bool value = true; };
 template <> struct CoopSupport<ThreeLink> { static constexpr bool value = true; };
+template <> struct CoopSupport<RoboticArm> { static constexpr bool value = true; };
 
 // Shared-memory layout (in reals) of the cooperative backward pass of ONE trajectory.
 template <class Mdl>
@@ -509,6 +511,179 @@ __device__ void colgroup_backward(const CoopTraj<R> (&tr)[4], int T, R* S, int l
         }
         if (!is_col && !is_aff) {
             CRL_UNROLL for (int i = 0; i < NS; ++i) Vc[i] = R(0);      // idle lanes stay at zero
+        }
+        // ---- output block
+        CRL_UNROLL for (int y = 0; y < 2; ++y) {
+            const R w2 = R(2.0 * Mdl::weight(NS));
+            vy[y] = (-w2) * pv[y] + w2 * yv[y];
+            vyy[y] = R(cost_hess<Mdl>(NS));
+        }
+    }
+    __syncwarp();
+}
+
+// -----------------------------------------------------------------------------------------
+// Column-group backward pass of the rigid two-link arm (RoboticArm): the same lane mapping as
+// colgroup_backward, but the Jacobian has dense variable rows (rows 1 and 3 of A and B), so
+//   A^T V, B^T V        combine rows 0..3 of the lane's own column with the step's A / B entries,
+//   (A^T V) A, (B^T V) A need ALL columns of A^T V / B^T V (24 shuffles),
+//   Quu                 needs columns 1 and 3 of B^T V.
+// The 16 variable entries of a time step (A[1][:], A[3][:], B[1][:], B[3][:], G) are precomputed for
+// all time steps in parallel (lanes over t; Mdl::coop_table).  Per element the operation sequence is
+// riccati_step's with the structural zeros / ones / h of RoboticArm::akind pruned the same way:
+// a product with the literal 1 (x * 1, fma(x, 1, acc)) stands for the plain copy / addition there.
+template <class R>
+__device__ void colgroup_backward_arm(const CoopTraj<R> (&tr)[4], int T, R* S, int lane) {
+    using Mdl = RoboticArm;
+    using CG = ColGroup<Mdl>;
+    constexpr int NS = Mdl::NS, M = Mdl::M, N = Mdl::N, D = Mdl::D, GS = CG::GS, NG = CG::NG, TAB = Mdl::kCoopTab;
+    static_assert(NS == 4 && M == 2 && TAB == 16, "written for the 4-state / 2-action arm");
+    const R h = R(kH);
+    const int g = lane / GS, c = lane % GS;
+    const bool is_col = c < NS, is_aff = c == NS, c_even_col = is_col && !(c & 1);
+    const int cc = is_col ? c : 0;
+
+    // ---- tables of the four trajectories: lanes take time steps lane, lane + 32, ...
+    CRL_UNROLL for (int q = 0; q < NG; ++q) {
+        for (int t = lane; t < T; t += 32) {
+            R xu[D], tab[TAB];
+            CRL_UNROLL for (int i = 0; i < D; ++i) xu[i] = tr[q].X[((size_t)t * D + i) * tr[q].xs];
+            Mdl::template coop_table<R>(xu, tab);
+            CRL_UNROLL for (int i = 0; i < TAB; ++i) tr[q].G[(size_t)t * TAB + i] = tab[i];
+        }
+    }
+    __syncwarp();
+
+    CoopTraj<R> me = tr[0];
+    CRL_UNROLL for (int q = 1; q < NG; ++q)
+        if (q == g) me = tr[q];
+    R* kst = (is_aff ? me.k : me.K + cc) + (size_t)(T - 1) * (is_aff ? M : M * NS);
+    const int kst_a = is_aff ? 1 : NS, kst_t = is_aff ? M : M * NS;
+
+    R Vc[NS], vy[2], vyy[2];
+    CRL_UNROLL for (int i = 0; i < NS; ++i) Vc[i] = R(0);
+    vy[0] = vy[1] = vyy[0] = vyy[1] = R(0);
+
+    // row values, one step ahead: the table (16), x_1, x_3 (cost gradient), u (2), output entries (2), targets (2)
+    R tb_n[TAB], xo_n[2], u_n[M], y_n[2], p_n[2];
+    {
+        const size_t r = (size_t)(T - 1), xs = (size_t)me.xs;
+        CRL_UNROLL for (int i = 0; i < TAB; ++i) tb_n[i] = me.G[r * TAB + i];
+        CRL_UNROLL for (int j = 0; j < 2; ++j) xo_n[j] = me.X[(r * D + 2 * j + 1) * xs];
+        CRL_UNROLL for (int a = 0; a < M; ++a) u_n[a] = me.X[(r * D + N + a) * xs];
+        CRL_UNROLL for (int y = 0; y < 2; ++y) { y_n[y] = me.X[(r * D + NS + y) * xs]; p_n[y] = me.prm.get(T - 1, y); }
+    }
+
+    for (int t = T - 1; t >= 0; --t) {
+        R A1[NS], A3[NS], B1[M], B3[M], G[2][2], xo[2], u[M], yv[2], pv[2];
+        CRL_UNROLL for (int j = 0; j < NS; ++j) { A1[j] = tb_n[j]; A3[j] = tb_n[NS + j]; }
+        CRL_UNROLL for (int a = 0; a < M; ++a) { B1[a] = tb_n[2 * NS + a]; B3[a] = tb_n[2 * NS + M + a]; }
+        G[0][0] = tb_n[12]; G[0][1] = tb_n[13]; G[1][0] = tb_n[14]; G[1][1] = tb_n[15];   // G[y][i/2] of the even columns
+        CRL_UNROLL for (int j = 0; j < 2; ++j) xo[j] = xo_n[j];
+        CRL_UNROLL for (int a = 0; a < M; ++a) u[a] = u_n[a];
+        CRL_UNROLL for (int y = 0; y < 2; ++y) { yv[y] = y_n[y]; pv[y] = p_n[y]; }
+        {
+            const size_t r = (size_t)(t > 0 ? t - 1 : 0), xs = (size_t)me.xs;
+            CRL_UNROLL for (int i = 0; i < TAB; ++i) tb_n[i] = me.G[r * TAB + i];
+            CRL_UNROLL for (int j = 0; j < 2; ++j) xo_n[j] = me.X[(r * D + 2 * j + 1) * xs];
+            CRL_UNROLL for (int a = 0; a < M; ++a) u_n[a] = me.X[(r * D + N + a) * xs];
+            CRL_UNROLL for (int y = 0; y < 2; ++y) { y_n[y] = me.X[(r * D + NS + y) * xs]; p_n[y] = me.prm.get((int)r, y); }
+        }
+        // ---- column c of A^T V and B^T V (affine lane: A^T v, B^T v); l ascending over the non-zero A[l][i]
+        R MA[NS], MB[M];
+        MA[0] = fmadd(Vc[3], A3[0], fmadd(Vc[1], A1[0], Vc[0]));
+        MA[1] = fmadd(Vc[3], A3[1], fmadd(Vc[1], A1[1], Vc[0] * h));
+        MA[2] = fmadd(Vc[3], A3[2], Vc[1] * A1[2] + Vc[2]);
+        MA[3] = fmadd(Vc[3], A3[3], fmadd(Vc[2], h, Vc[1] * A1[3]));
+        CRL_UNROLL for (int a = 0; a < M; ++a) MB[a] = fmadd(Vc[3], B3[a], Vc[1] * B1[a]);
+        // ---- Quu from columns 1 and 3, factored by every lane
+        R Quu[M][M];
+        CRL_UNROLL for (int a = 0; a < M; ++a) {
+            const R m1 = __shfl_sync(0xffffffffu, MB[a], 1, GS), m3 = __shfl_sync(0xffffffffu, MB[a], 3, GS);
+            CRL_UNROLL for (int b = 0; b < M; ++b) {
+                const R acc = fmadd(m3, B3[b], m1 * B1[b]);
+                Quu[a][b] = (a == b) ? R(cost_hess<Mdl>(N + a)) + acc : acc;
+            }
+        }
+        LuFactors<M, R> lu;
+        lu_factor<M, R>(Quu, lu);
+        // ---- column c of [Qss | qs] and [Qus | qu]: sum over k of (row)[k] * A[k][c], k ascending over the
+        //      non-zero A[k][c]: c < 2: k = 0 (1 or h), 1, 3;  c >= 2: k = 1, 2 (1 or h), 3
+        const bool lo = cc < 2;
+        R a1c = A1[0], a3c = A3[0];
+        CRL_UNROLL for (int j = 1; j < NS; ++j) { a1c = (cc == j) ? A1[j] : a1c; a3c = (cc == j) ? A3[j] : a3c; }
+        const R c_first = lo ? ((cc == 0) ? R(1) : h) : a1c;      // coefficient of the first term
+        const R c_second = lo ? a1c : ((cc == 2) ? R(1) : h);      // coefficient of the second term
+        const R Gc[2] = {(cc == 2) ? G[0][1] : G[0][0], (cc == 2) ? G[1][1] : G[1][0]};
+        R Qx[NS], Qu[M][1];
+        CRL_UNROLL for (int i = 0; i < NS; ++i) {
+            const R r0 = __shfl_sync(0xffffffffu, MA[i], 0, GS), r1 = __shfl_sync(0xffffffffu, MA[i], 1, GS);
+            const R r2 = __shfl_sync(0xffffffffu, MA[i], 2, GS), r3 = __shfl_sync(0xffffffffu, MA[i], 3, GS);
+            R acc = (lo ? r0 : r1) * c_first;
+            acc = fmadd(lo ? r1 : r2, c_second, acc);
+            acc = fmadd(r3, a3c, acc);
+            R aff = MA[i];
+            if (!(i & 1)) {
+                R ag = fmadd(G[0][i / 2] * vyy[0], Gc[0], acc);
+                ag = fmadd(G[1][i / 2] * vyy[1], Gc[1], ag);
+                acc = c_even_col ? ag : acc;
+                aff = fmadd(vy[0], G[0][i / 2], aff);
+                aff = fmadd(vy[1], G[1][i / 2], aff);
+            }
+            const R hess = (i & 1) ? R(cost_hess<Mdl>(1)) : R(cost_hess<Mdl>(0));
+            const R diag = hess + acc;
+            const R grad = (i & 1) ? R(2.0 * Mdl::weight(1)) * xo[i / 2] : R(0.0);
+            Qx[i] = is_aff ? grad + aff : ((i == c) ? diag : acc);
+        }
+        CRL_UNROLL for (int a = 0; a < M; ++a) {
+            const R r0 = __shfl_sync(0xffffffffu, MB[a], 0, GS), r1 = __shfl_sync(0xffffffffu, MB[a], 1, GS);
+            const R r2 = __shfl_sync(0xffffffffu, MB[a], 2, GS), r3 = __shfl_sync(0xffffffffu, MB[a], 3, GS);
+            R col = (lo ? r0 : r1) * c_first;
+            col = fmadd(lo ? r1 : r2, c_second, col);
+            col = fmadd(r3, a3c, col);
+            const R aff = R(2.0 * Mdl::weight(N)) * u[a] + MB[a];
+            Qu[a][0] = is_aff ? aff : col;
+        }
+        // ---- gains of this column
+        R Kc[M][1];
+        CRL_UNROLL for (int a = 0; a < M; ++a) Kc[a][0] = Qu[a][0];
+        lu_apply<M, 1, R>(lu, Kc);
+        CRL_UNROLL for (int a = 0; a < M; ++a) Kc[a][0] = -Kc[a][0];
+        if (is_col || is_aff) {
+            CRL_UNROLL for (int a = 0; a < M; ++a) kst[a * kst_a] = Kc[a][0];
+        }
+        kst -= kst_t;
+        // ---- new column: rows i <= c of V (affine lane: all of v)
+        R Vn[NS];
+        CRL_UNROLL for (int i = 0; i < NS; ++i) {
+            R Ki[M], Ui[M], W[M];
+            CRL_UNROLL for (int a = 0; a < M; ++a) {
+                Ki[a] = __shfl_sync(0xffffffffu, Kc[a][0], i, GS);
+                Ui[a] = __shfl_sync(0xffffffffu, Qu[a][0], i, GS);
+            }
+            CRL_UNROLL for (int b = 0; b < M; ++b) {
+                R acc = Ki[0] * Quu[0][b];
+                CRL_UNROLL for (int a = 1; a < M; ++a) acc = fmadd(Ki[a], Quu[a][b], acc);
+                W[b] = acc;
+            }
+            R sij = Ui[0] * Kc[0][0], sji = Qu[0][0] * Ki[0], rr = W[0] * Kc[0][0];
+            CRL_UNROLL for (int a = 1; a < M; ++a) {
+                sij = fmadd(Ui[a], Kc[a][0], sij);
+                sji = fmadd(Qu[a][0], Ki[a], sji);
+                rr = fmadd(W[a], Kc[a][0], rr);
+            }
+            Vn[i] = ((Qx[i] + sij) + sji) + rr;
+        }
+        // ---- mirror: V(i, c) for i > c is column i's row c
+        R* Sb = S + (t & 1) * (NG * NS * GS) + g * (NS * GS);
+        CRL_UNROLL for (int i = 0; i < NS; ++i) Sb[i * GS + c] = Vn[i];
+        __syncwarp();
+        CRL_UNROLL for (int i = 0; i < NS; ++i) {
+            const R low = Sb[cc * GS + i];
+            Vc[i] = (is_col && i > c) ? low : Vn[i];
+        }
+        if (!is_col && !is_aff) {
+            CRL_UNROLL for (int i = 0; i < NS; ++i) Vc[i] = R(0);
         }
         // ---- output block
         CRL_UNROLL for (int y = 0; y < 2; ++y) {

@@ -424,10 +424,19 @@ __device__ __noinline__ double coop_rollout(const R* X, const R* K, const R* k, 
 }
 
 // NT == 4: the column-group pass (8 lanes per trajectory); otherwise the element-per-lane pass
+// the element-per-lane pass exists for the kinematic chains only
+template <class Mdl> struct HasElementPass { static constexpr bool value = true; };
+template <> struct HasElementPass<RoboticArm> { static constexpr bool value = false; };
+
 template <class Mdl, class R, int NT>
 __device__ __noinline__ void coop_backward_call(const CoopTraj<R> (&tr)[NT], int T, R* S, int lane) {
-    if constexpr (NT == ColGroup<Mdl>::NG) colgroup_backward<Mdl, R>(tr, T, S, lane);
-    else coop_backward<Mdl, R, NT>(tr, T, S, lane);
+    if constexpr (NT == ColGroup<Mdl>::NG) {
+        if constexpr (HasElementPass<Mdl>::value) colgroup_backward<Mdl, R>(tr, T, S, lane);
+        else colgroup_backward_arm<R>(tr, T, S, lane);
+    } else {
+        static_assert(HasElementPass<Mdl>::value, "this model only has the column-group pass (NT = 4)");
+        coop_backward<Mdl, R, NT>(tr, T, S, lane);
+    }
 }
 
 // shared memory (reals) one warp of the engine needs
@@ -452,7 +461,7 @@ __host__ __device__ constexpr long long coop_xscr_reals(int T) {
 }
 template <class Mdl>
 __host__ __device__ constexpr long long coop_gscr_reals_per_traj(int T) {
-    return (long long)T * (Mdl::M * Mdl::NS + Mdl::M + 2 * Mdl::M);
+    return (long long)T * (Mdl::M * Mdl::NS + Mdl::M + Mdl::kCoopTab);
 }
 template <class Mdl, int NT>
 __host__ __device__ constexpr long long coop_scratch_reals(int T) {
@@ -651,15 +660,18 @@ __device__ void coop_engine(const SolveArgs<R>& a, Source& src, R* xscr, R* gscr
             int n_on = 0, q_on = 0;
             CRL_UNROLL for (int q = 0; q < NT; ++q)
                 if (tr[q].on) { ++n_on; q_on = q; }
-            if (NT > 1 && n_on == 1) {
-                CoopTraj<R> one[1];
-                one[0] = tr[0];
-                CRL_UNROLL for (int q = 1; q < NT; ++q)
-                    if (q == q_on) one[0] = tr[q];
-                coop_backward_call<Mdl, R, 1>(one, T, S, lane);
-            } else {
-                coop_backward_call<Mdl, R, NT>(tr, T, S, lane);
+            bool alone = false;
+            if constexpr (NT > 1 && HasElementPass<Mdl>::value) {
+                if (n_on == 1) {
+                    CoopTraj<R> one[1];
+                    one[0] = tr[0];
+                    CRL_UNROLL for (int q = 1; q < NT; ++q)
+                        if (q == q_on) one[0] = tr[q];
+                    coop_backward_call<Mdl, R, 1>(one, T, S, lane);
+                    alone = true;
+                }
             }
+            if (!alone) coop_backward_call<Mdl, R, NT>(tr, T, S, lane);
         }
         __syncwarp();
         tm.lap(PH_COOP_BACKWARD);

@@ -49,6 +49,21 @@ struct KinematicArm {
     CRL_HD static constexpr double u_lo(int) { return -100.0; }
     CRL_HD static constexpr double u_hi(int) { return 100.0; }
 
+    // per-time-step table of the cooperative backward pass (ilqr_coop.cuh): the variable Jacobian entries
+    // G[0][0], G[0][2], ..., G[1][0], G[1][2], ...
+    static constexpr int kCoopTab = 2 * J;
+    template <class R>
+    CRL_HD static void coop_table(const R* xu, R* tab) {
+        R ang[J], sn[J], cs[J], G[2][NS];
+        angles<R>(xu, ang);
+        sincos_batch<J, R>(ang, sn, cs);
+        jac_trig<R>(xu, sn, cs, nullptr, nullptr, G);
+        CRL_UNROLL for (int i = 0; i < J; ++i) {
+            tab[i] = G[0][2 * i];
+            tab[J + i] = G[1][2 * i];
+        }
+    }
+
     // angles whose sin/cos one time step needs: the cumulative joint angles
     static constexpr int NANG = J;
     template <class R>
@@ -229,6 +244,20 @@ struct RoboticArm {
         G[0][2] = R(2.0) * t.c2;
         G[1][0] = -t.s1;
         G[1][2] = R(-2.0) * t.s2;
+    }
+
+    // per-time-step table of the cooperative backward pass: A[1][0..3], A[3][0..3], B[1][0..1], B[3][0..1],
+    // G[0][0], G[0][2], G[1][0], G[1][2]
+    static constexpr int kCoopTab = 16;
+    template <class R>
+    CRL_HD static void coop_table(const R* xu, R* tab) {
+        R ang[NANG], sn[NANG], cs[NANG], A[NS][NS], B[NS][M], G[NO][NS];
+        angles<R>(xu, ang);
+        sincos_batch<NANG, R>(ang, sn, cs);
+        jac_trig<R>(xu, sn, cs, A, B, G);
+        CRL_UNROLL for (int j = 0; j < NS; ++j) { tab[j] = A[1][j]; tab[NS + j] = A[3][j]; }
+        CRL_UNROLL for (int a = 0; a < M; ++a) { tab[2 * NS + a] = B[1][a]; tab[2 * NS + M + a] = B[3][a]; }
+        tab[12] = G[0][0]; tab[13] = G[0][2]; tab[14] = G[1][0]; tab[15] = G[1][2];
     }
 
     CRL_HD static double cost(const double* x, const double* p) {

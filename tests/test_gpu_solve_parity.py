@@ -220,7 +220,8 @@ def test_full_size_properties():
 
 
 @pytest.mark.parametrize("model,B,T", [("ThreeLinkPlanarManipulator", 4096, 100), ("TwoLinkPlanarManipulator", 2048, 60),
-                                       ("ThreeLinkPlanarManipulator", 5, 100)])
+                                       ("ThreeLinkPlanarManipulator", 5, 100), ("RoboticArmTracking", 2048, 120),
+                                       ("RoboticArmTracking", 3, 200)])
 def test_every_scheduling_path_gives_the_same_bits(model, B, T):
     """Results must not depend on which path finished a trajectory: lane-per-trajectory kernel only,
     lane kernel with the cooperative tail (default and 'everything after the queue drains'),

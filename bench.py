@@ -218,7 +218,7 @@ def workload_config(args, n_gpus):
                 "to convergence (relative 1e-6, max_iter 1000)" if args.mode == "converge" else "fixed work (20 iterations)"),
             "model": args.model, "batch_per_gpu": args.batch, "global_batch": args.batch * n_gpus, "horizon": args.horizon,
             "mode": args.mode, "parallelism": "dp%d (independent shards, terminal gather of J/iters/flags)" % n_gpus,
-            "cache": "working set (solver workspace ~1.3 GB + 0.6 GB results) exceeds the 126 MB L2; "
+            "cache": "working set (solver workspace ~2.1 GB + 0.6 GB results) exceeds the 126 MB L2; "
                      "a 512 MB buffer is overwritten between timed steps"}
 
 

@@ -95,3 +95,19 @@ def test_synthetic_generator_known_values():
     xr, _ = synthetic_batch("RoboticArmTracking", 4, seed=1)
     assert np.allclose(xr[:, 5], np.cos(xr[:, 0]) + 2 * np.cos(xr[:, 2]))
     assert np.all(np.hypot(t3[:, 0], t3[:, 1]) <= 5.0)
+
+
+def test_scheduling_options_reach_the_c_abi_struct():
+    """coop_threshold / occupancy are scheduling knobs only: defaulted, forwarded into crl_solver_opts, and the
+    ctypes struct has the ABI-v2 layout of include/curiousrl_b200.h (no GPU needed)."""
+    import ctypes
+    from curiousrl_b200 import _native
+    from curiousrl_b200.algorithm.ilqr_solver import BasiciLQR
+    names = [f[0] for f in _native.SolverOpts._fields_]
+    assert names == ["max_iter", "is_check_stop", "stopping_criterion", "max_line_search", "gamma", "line_search_method",
+                     "stopping_method", "grid_blocks", "reserved", "coop_threshold", "reserved2"]
+    assert ctypes.sizeof(_native.SolverOpts) == 56
+    sig = inspect.signature(BasiciLQR.__init__).parameters
+    assert sig["coop_threshold"].default == 0 and sig["occupancy"].default == 0
+    o = BasiciLQR(max_line_search=10, coop_threshold=-1, occupancy=20)._opts(max_iter=7, is_check_stop=False)
+    assert (o.max_iter, o.is_check_stop, o.max_line_search, o.reserved, o.coop_threshold, o.reserved2) == (7, 0, 10, 20, -1, 0)

@@ -253,3 +253,16 @@ def test_cooperative_paths_fixed_work_and_line_search_modes():
             res = make_algo(model, T, verify=False, **kw, **extra).solve_batch(x0, tgt, trace=True)
             for f in ("iterations", "converged", "obj_fun_value", "trajectory", "alpha_trace"):
                 assert torch.equal(getattr(res, f), getattr(ref, f)), "%s differs with %s %s" % (f, kw, extra)
+
+
+@pytest.mark.parametrize("model", ["ThreeLinkPlanarManipulator", "TwoLinkPlanarManipulator", "RoboticArmTracking"])
+@pytest.mark.parametrize("T", [1, 2, 3, 33])
+def test_scheduling_paths_at_tiny_horizons(model, T):
+    """Degenerate horizons (T = 1: no action is ever applied) through every path."""
+    from curiousrl_b200.utils.synthetic import synthetic_batch
+    x0, tgt = synthetic_batch(model, 70, seed=11)
+    ref = make_algo(model, T, verify=False, coop_threshold=-1, max_iter=30).solve_batch(x0, tgt, trace=True)
+    for kw in (dict(), dict(coop_threshold=32), dict(occupancy=20)):
+        res = make_algo(model, T, verify=False, max_iter=30, **kw).solve_batch(x0, tgt, trace=True)
+        for f in ("iterations", "converged", "obj_fun_value", "trajectory", "alpha_trace"):
+            assert torch.equal(getattr(res, f), getattr(ref, f)), "%s differs with %s at T=%d" % (f, kw, T)

@@ -150,4 +150,20 @@ struct View {
     CRL_HD static void st(R* row, int c, R v) { row[c * SC] = v; }
 };
 
+// One trajectory whose rows are contiguous but RS reals apart: element (t, c) at base[t * RS + c].
+// The cooperative engine's line-search buffers are [T][candidates][DP] (DP = row length padded to a
+// multiple of 32 bytes), so a candidate's row is a run of whole 32-byte sectors: reading the current
+// trajectory touches only its own bytes (an element-interleaved layout costs a sector per element).
+// `on` = false turns the stores off (a candidate that is evaluated for its cost only).
+template <class R, int RS>
+struct RowView {
+    R* base;
+    bool on = true;
+    CRL_HD R* row(int t) const { return base + (size_t)t * RS; }
+    CRL_HD static R ld(const R* row, int c) { return row[c]; }
+    CRL_HD void st(R* row, int c, R v) const {
+        if (on) row[c] = v;
+    }
+};
+
 }  // namespace crl

@@ -48,9 +48,9 @@ struct Bounds {
 // Quirk kept: row t is clamped only AFTER it produced row t+1, and row T-1 is never clamped
 // (ilqr_dynamic_model.py:104-108).  State bounds are +-inf in all three scenarios.
 // Returns J = sum_t l(X[t]) of the stored trajectory.
-template <class Mdl, class R, int SC>
-CRL_HD double rollout_open(const R* x0, int sx0, const R* U, int su_t, const ParamRef<R>& prm,
-                           const Bounds<R>& ub, int T, View<R, Mdl::D, SC> X) {
+template <class Mdl, class R, class XV>
+CRL_HD double rollout_open_v(const R* x0, int sx0, const R* U, int su_t, const ParamRef<R>& prm,
+                             const Bounds<R>& ub, int T, XV X) {
     constexpr int N = Mdl::N, M = Mdl::M, D = Mdl::D;
     R xu[D], xn[N];
     CRL_UNROLL for (int i = 0; i < N; ++i) xu[i] = x0[i * sx0];
@@ -71,6 +71,12 @@ CRL_HD double rollout_open(const R* x0, int sx0, const R* U, int su_t, const Par
         }
     }
     return J;
+}
+
+template <class Mdl, class R, int SC>
+CRL_HD double rollout_open(const R* x0, int sx0, const R* U, int su_t, const ParamRef<R>& prm,
+                           const Bounds<R>& ub, int T, View<R, Mdl::D, SC> X) {
+    return rollout_open_v<Mdl, R>(x0, sx0, U, su_t, prm, ub, T, X);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -105,9 +111,9 @@ struct DirectFeed {
 
 // Closed-loop rollout  u = u_old + K (x_new - x_old) + alpha k  for one step size
 // (ilqr_dynamic_model.py:111-134) with the cost of the new trajectory (ilqr_obj_fun.py:86-95).
-template <class Mdl, class R, class Feed, int SCXN>
+template <class Mdl, class R, class Feed, class XV>
 CRL_HD double rollout_closed_f(Feed& feed, R alpha, const ParamRef<R>& prm, const Bounds<R>& ub, int T,
-                               View<R, Mdl::D, SCXN> Xnew) {
+                               XV Xnew) {
     constexpr int N = Mdl::N, M = Mdl::M, D = Mdl::D, KN = Feed::kKN;
     R xu[D], xn[N];
     feed.begin(T - 1);

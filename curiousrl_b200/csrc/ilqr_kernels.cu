@@ -409,28 +409,35 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
 //                    this way - lowest latency per iteration, used when the batch is too small
 //                    to amortise the lane-per-trajectory kernel's long tail);
 //   StragglerSource  the straggler queue of the lane-per-trajectory kernel (its tail).
-// Scratch of one warp: xscr = per trajectory two line-search buffers [T][D][GL] (the GL candidates of
-// a pass side by side, so that the lanes of a trajectory store 8 * GL consecutive bytes; the current
-// trajectory is one column of one of them, element stride GL); gscr = per trajectory K [T][M*NS],
-// k [T][M], G table [T][2J].
+// Scratch of one warp: xscr = per trajectory two line-search buffers [T][GL][DP] (the GL candidates of
+// a pass side by side; DP = D padded to whole 32-byte sectors, so a candidate's row is a run of sectors
+// of its own and the current trajectory - one candidate of one of the buffers, row stride GL * DP - is
+// read without touching the other candidates' bytes; an element-interleaved [T][D][GL] layout moved a
+// sector per element, 4-8x the bytes); gscr = per trajectory K [T][M*NS], k [T][M], G table [T][2J].
+// Candidates kCoopStore.. of a pass (step sizes accepted in < 1 % of the iterations) are evaluated for
+// their cost only; if one of them wins, the first lane of the group replays it into candidate 0.
 
 // closed-loop rollout for one step size from a stride-XS trajectory, stored to a stride-XS column;
 // returns its cost (a separate function so that it gets its own register allocation)
-template <class Mdl, class R, int XS>
+template <class Mdl, class R, int RS>
 __device__ __noinline__ double coop_rollout(const R* X, const R* K, const R* k, R alpha, ParamRef<R> prm, Bounds<R> ub,
-                                            int T, R* Xnew) {
-    RowPrefetchFeed<Mdl, R, XS> feed(X, K, k);
-    return rollout_closed_f<Mdl, R>(feed, alpha, prm, ub, T, View<R, Mdl::D, XS>{Xnew});
+                                            int T, R* Xnew, bool store) {
+    RowPrefetchFeed<Mdl, R, RS> feed(X, K, k);
+    return rollout_closed_f<Mdl, R>(feed, alpha, prm, ub, T, RowView<R, RS>{Xnew, store});
 }
 
-// NT == 4: the column-group pass (8 lanes per trajectory); otherwise the element-per-lane pass
+// NT == 8: the pair-group pass (4 lanes per trajectory, kinematic chains); NT == 4: the column-group pass
+// (8 lanes per trajectory); otherwise the element-per-lane pass
 // the element-per-lane pass exists for the kinematic chains only
 template <class Mdl> struct HasElementPass { static constexpr bool value = true; };
 template <> struct HasElementPass<RoboticArm> { static constexpr bool value = false; };
 
 template <class Mdl, class R, int NT>
 __device__ __noinline__ void coop_backward_call(const CoopTraj<R> (&tr)[NT], int T, R* S, int lane) {
-    if constexpr (NT == ColGroup<Mdl>::NG) {
+    if constexpr (NT == 8) {
+        static_assert(HasElementPass<Mdl>::value, "the pair-group pass (NT = 8) is written for the kinematic chains");
+        pairgroup_backward<Mdl, R>(tr, T, S, lane);
+    } else if constexpr (NT == ColGroup<Mdl>::NG) {
         if constexpr (HasElementPass<Mdl>::value) colgroup_backward<Mdl, R>(tr, T, S, lane);
         else colgroup_backward_arm<R>(tr, T, S, lane);
     } else {
@@ -442,22 +449,39 @@ __device__ __noinline__ void coop_backward_call(const CoopTraj<R> (&tr)[NT], int
 // shared memory (reals) one warp of the engine needs
 template <class Mdl, int NT>
 __host__ __device__ constexpr int coop_smem_reals() {
-    return NT == ColGroup<Mdl>::NG ? (ColGroup<Mdl>::SMEM > CoopLayout<Mdl>::SZ ? ColGroup<Mdl>::SMEM : CoopLayout<Mdl>::SZ)
-                                   : NT * CoopLayout<Mdl>::SZ;
+    return NT == 8 ? (PairGroup<Mdl>::SMEM > CoopLayout<Mdl>::SZ ? PairGroup<Mdl>::SMEM : CoopLayout<Mdl>::SZ)
+           : NT == ColGroup<Mdl>::NG
+               ? (ColGroup<Mdl>::SMEM > CoopLayout<Mdl>::SZ ? ColGroup<Mdl>::SMEM : CoopLayout<Mdl>::SZ)
+               : NT * CoopLayout<Mdl>::SZ;
 }
 
-#ifndef CRL_COOP_NT
-#define CRL_COOP_NT 4
+// Trajectories a warp iterates together in the cooperative engine: 4 (column-group backward pass, 8
+// line-search lanes per trajectory).  8 (pair-group pass, 4 line-search lanes; kinematic chains only) was
+// measured too: as the whole solve it is 4 % faster in fixed-work runs (backward -31 %, but 1.8 line-search
+// passes per iteration instead of 1), as the tail of the lane kernel 15 % slower - the tail is bound by the
+// latency of an iteration, and an iteration of eight takes twice as long as an iteration of four.
+#ifdef CRL_COOP_NT
+template <class Mdl> constexpr int kCoopNTFor = CRL_COOP_NT;
+#else
+template <class Mdl> constexpr int kCoopNTFor = 4;
 #endif
-constexpr int kCoopNT = CRL_COOP_NT;         // trajectories a warp iterates together in the cooperative engine
 
 template <int NT>
 struct CoopGeom {
     static constexpr int GL = (32 / NT) > 16 ? 16 : (32 / NT);   // line-search lanes (= candidates per pass) per trajectory
 };
+// row length of a candidate in the line-search buffers: D padded to a multiple of 4 reals (32 bytes in FP64)
+template <class Mdl>
+__host__ __device__ constexpr int coop_dp() { return (Mdl::D + 3) & ~3; }
+// reals between consecutive time steps of one candidate
+template <class Mdl, int NT>
+__host__ __device__ constexpr int coop_rs() { return CoopGeom<NT>::GL * coop_dp<Mdl>(); }
+// candidates of a pass that are stored (the rest: cost only)
+template <int NT>
+__host__ __device__ constexpr int coop_store() { return CoopGeom<NT>::GL == 8 ? 6 : CoopGeom<NT>::GL; }
 template <class Mdl, int NT>
 __host__ __device__ constexpr long long coop_xscr_reals(int T) {
-    return (long long)NT * 2 * CoopGeom<NT>::GL * T * Mdl::D;
+    return (long long)NT * 2 * T * coop_rs<Mdl, NT>();
 }
 template <class Mdl>
 __host__ __device__ constexpr long long coop_gscr_reals_per_traj(int T) {
@@ -472,7 +496,7 @@ __host__ __device__ constexpr long long coop_scratch_reals(int T) {
 // the engine it becomes in the tail.
 template <class Mdl>
 __host__ __device__ constexpr long long slot_reals(int T) {
-    return lane_tiles_reals<Mdl>(T) + (CoopSupport<Mdl>::value ? coop_scratch_reals<Mdl, kCoopNT>(T) : 0);
+    return lane_tiles_reals<Mdl>(T) + (CoopSupport<Mdl>::value ? coop_scratch_reals<Mdl, kCoopNTFor<Mdl>>(T) : 0);
 }
 
 // Source of fresh trajectories: the batch itself.
@@ -486,7 +510,7 @@ struct BatchSource {
     template <int NT>
     __device__ unsigned take(unsigned empty, R* const (&dst)[NT], long long (&traj)[NT], int (&it)[NT], double (&J)[NT],
                              int lane) {
-        constexpr int GL = CoopGeom<NT>::GL;
+        constexpr int RS = coop_rs<Mdl, NT>();
         if (exhausted || empty == 0u) return 0u;
         const int want = __popc(empty);
         unsigned long long base = 0;
@@ -509,8 +533,8 @@ struct BatchSource {
         CRL_UNROLL for (int q = 0; q < NT; ++q) {
             if (lane == q && ((got >> q) & 1u)) {
                 const long long idx = traj[q];
-                rollout_open<Mdl, R, GL>(a.x0 + idx * Mdl::N, 1, a.u0 ? a.u0 + idx * a.u0_sb : nullptr, Mdl::M, a.pb.prm(idx),
-                                         a.pb.ub, a.pb.T, View<R, Mdl::D, GL>{dst[q]});
+                rollout_open_v<Mdl, R>(a.x0 + idx * Mdl::N, 1, a.u0 ? a.u0 + idx * a.u0_sb : nullptr, Mdl::M, a.pb.prm(idx),
+                                       a.pb.ub, a.pb.T, RowView<R, RS>{dst[q]});
             }
         }
         __syncwarp();
@@ -525,14 +549,14 @@ template <class Mdl, class R>
 struct StragglerSource {
     const SolveArgs<R>& a;
     unsigned total_warps;
-    long long claim[4] = {-1, -1, -1, -1};                            // queue index claimed for slot q, not yet published
+    long long claim[8] = {-1, -1, -1, -1, -1, -1, -1, -1};            // queue index claimed for slot q, not yet published
     __device__ StragglerSource(const SolveArgs<R>& a_, unsigned tw) : a(a_), total_warps(tw) {}
     bool closed = false;
     unsigned long long q_tail = 0, q_head = 0;
     template <int NT>
     __device__ unsigned take(unsigned empty, R* const (&dst)[NT], long long (&traj)[NT], int (&it)[NT], double (&J)[NT],
                              int lane) {
-        static_assert(NT <= 4, "claim slots");
+        static_assert(NT <= 8, "claim slots");
         unsigned long long q_done = 0, q_fin = 0;
         if (lane == 0) {
             q_done = ld_volatile_u64(a.ctl + kCtlDone);
@@ -589,7 +613,8 @@ struct StragglerSource {
             J[q] = __ldcg(&qe->J_last);
             it[q] = __ldcg(&qe->it);
             const int n = a.pb.T * Mdl::D;
-            for (int e = lane; e < n; e += 32) dst[q][(size_t)e * CoopGeom<NT>::GL] = __ldcg(src + (size_t)e * 32);
+            for (int e = lane; e < n; e += 32)
+                dst[q][(size_t)(e / Mdl::D) * coop_rs<Mdl, NT>() + e % Mdl::D] = __ldcg(src + (size_t)e * 32);
             claim[q] = -1;
             got |= 1u << q;
         }
@@ -598,7 +623,7 @@ struct StragglerSource {
     }
     __device__ bool drained(int) const {
         bool pending = false;
-        CRL_UNROLL for (int q = 0; q < 4; ++q) pending = pending || claim[q] >= 0;
+        CRL_UNROLL for (int q = 0; q < 8; ++q) pending = pending || claim[q] >= 0;
         return closed && !pending && q_head >= q_tail;
     }
     __device__ void finished(int n, int lane) {
@@ -609,13 +634,14 @@ struct StragglerSource {
 template <class Mdl, class R, int NT, class Source>
 __device__ void coop_engine(const SolveArgs<R>& a, Source& src, R* xscr, R* gscr, R* S, int lane, PhaseTimer& tm) {
     constexpr int M = Mdl::M, D = Mdl::D, NS = Mdl::NS, GL = CoopGeom<NT>::GL;
+    constexpr int DP = coop_dp<Mdl>(), RS = coop_rs<Mdl, NT>(), NST = coop_store<NT>();
     const int T = a.pb.T;
     const size_t TD = (size_t)T * D, TK = (size_t)T * M * NS, Tk = (size_t)T * M;
     const size_t TGS = (size_t)coop_gscr_reals_per_traj<Mdl>(T);
-    const size_t BUF = TD * GL;                               // one line-search buffer [T][D][GL]
+    const size_t BUF = (size_t)T * RS;                        // one line-search buffer [T][GL][DP]
     const int tries = (a.op.ls_method == CRL_LS_NONE) ? 1 : a.op.max_ls;
     const bool feas = a.op.ls_method == CRL_LS_FEASIBILITY;
-    // slot state, identical in every lane: the current trajectory of slot q is column s_col[q] of its buffer s_buf[q]
+    // slot state, identical in every lane: the current trajectory of slot q is candidate s_col[q] of its buffer s_buf[q]
     long long s_traj[NT];
     int s_it[NT], s_buf[NT], s_col[NT];
     double s_J[NT];
@@ -647,8 +673,8 @@ __device__ void coop_engine(const SolveArgs<R>& a, Source& src, R* xscr, R* gscr
         CRL_UNROLL for (int q = 0; q < NT; ++q) {
             const bool on = s_traj[q] >= 0;
             R* g = gscr + (size_t)q * TGS;
-            tr[q].X = xscr + (size_t)(2 * q + s_buf[q]) * BUF + s_col[q];
-            tr[q].xs = GL;
+            tr[q].X = xscr + (size_t)(2 * q + s_buf[q]) * BUF + s_col[q] * DP;
+            tr[q].rs = RS;
             tr[q].prm = a.pb.prm(on ? s_traj[q] : 0);
             tr[q].K = g;
             tr[q].k = g + TK;
@@ -702,8 +728,8 @@ __device__ void coop_engine(const SolveArgs<R>& a, Source& src, R* xscr, R* gscr
             if (ls_lane && my_pend && idx < tries) {
                 double al = 1.0;
                 for (int i = 0; i < idx; ++i) al = al * a.op.gamma;
-                Jt = coop_rollout<Mdl, R, GL>(mt.X, mt.K, mt.k, (R)al, mt.prm, a.pb.ub, T,
-                                              xscr + (size_t)(2 * q_ls + (my_buf ^ 1)) * BUF + c_ls);
+                Jt = coop_rollout<Mdl, R, RS>(mt.X, mt.K, mt.k, (R)al, mt.prm, a.pb.ub, T,
+                                              xscr + (size_t)(2 * q_ls + (my_buf ^ 1)) * BUF + c_ls * DP, c_ls < NST);
                 ok = (a.op.ls_method == CRL_LS_NONE) || ls_accept(Jt, my_Jl, feas);
             }
             const unsigned okm = __ballot_sync(kFull, ok);
@@ -722,6 +748,25 @@ __device__ void coop_engine(const SolveArgs<R>& a, Source& src, R* xscr, R* gscr
                         next[q] += GL;
                     }
                 }
+            }
+        }
+        if constexpr (NST < GL) {
+            // a winner among the cost-only candidates: the first lane of its group replays it into candidate 0
+            bool need = false;
+            CRL_UNROLL for (int q = 0; q < NT; ++q) need = need || (accepted[q] && newcol[q] >= NST);
+            if (need) {
+                int my_taken = -1, my_buf = 0;
+                CoopTraj<R> mt = tr[0];
+                CRL_UNROLL for (int q = 0; q < NT; ++q)
+                    if (q == q_ls && accepted[q] && newcol[q] >= NST) { my_taken = taken[q]; my_buf = s_buf[q]; mt = tr[q]; }
+                if (ls_lane && c_ls == 0 && my_taken >= 0) {
+                    double al = 1.0;
+                    for (int i = 0; i < my_taken; ++i) al = al * a.op.gamma;
+                    coop_rollout<Mdl, R, RS>(mt.X, mt.K, mt.k, (R)al, mt.prm, a.pb.ub, T,
+                                             xscr + (size_t)(2 * q_ls + (my_buf ^ 1)) * BUF, true);
+                }
+                CRL_UNROLL for (int q = 0; q < NT; ++q)
+                    if (accepted[q] && newcol[q] >= NST) newcol[q] = 0;
             }
         }
         __syncwarp();
@@ -745,9 +790,9 @@ __device__ void coop_engine(const SolveArgs<R>& a, Source& src, R* xscr, R* gscr
                     a.conv_out[s_traj[q]] = (stop && a.op.check_stop) ? 1 : 0;
                 }
                 if (a.X_out) {
-                    const R* from = xscr + (size_t)(2 * q + s_buf[q]) * BUF + s_col[q];
+                    const R* from = xscr + (size_t)(2 * q + s_buf[q]) * BUF + s_col[q] * DP;
                     R* to = a.X_out + s_traj[q] * TD;
-                    for (int e = lane; e < T * D; e += 32) to[e] = from[(size_t)e * GL];
+                    for (int e = lane; e < T * D; e += 32) to[e] = from[(size_t)(e / D) * RS + e % D];
                     __syncwarp();                               // the buffers are reused by the slot's next trajectory
                 }
                 s_traj[q] = -1;
@@ -788,7 +833,7 @@ __device__ void publish_stragglers(const SolveArgs<R>& a, bool live, long long t
 
 
 // The whole solve by the cooperative engine: persistent grid, WARPS warps per CTA, every warp
-// takes kCoopNT trajectories of the batch at a time.
+// takes NT trajectories of the batch at a time.
 template <class Mdl, class R, int WARPS, int MINB, int NT>
 __global__ void __launch_bounds__(WARPS * 32, MINB) coop_solve_kernel(SolveArgs<R> a) {
     extern __shared__ __align__(16) unsigned char coop_smem[];
@@ -1133,11 +1178,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) solve_kernel(SolveArgs<R> a)
         // sit in tile `cur`) and then serves it; the other X tile and the gain tiles are its scratch.
         const View<R, D, 32> Xc = cur ? Xbuf1 : Xbuf0;
         R* const xfree = a.ws + slot * a.slot_elems + lane_tiles_reals<Mdl>(T);   // engine scratch behind the tiles
-        R* const gfree = xfree + coop_xscr_reals<Mdl, kCoopNT>(T);
+        R* const gfree = xfree + coop_xscr_reals<Mdl, kCoopNTFor<Mdl>>(T);
         publish_stragglers<R>(a, traj >= 0, traj, it, J_last, Xc.base, lane);
         tm.lap(PH_RETIRE);
         StragglerSource<Mdl, R> src(a, gridDim.x * WARPS);
-        coop_engine<Mdl, R, kCoopNT>(a, src, xfree, gfree, stage_sm, lane, tm);
+        coop_engine<Mdl, R, kCoopNTFor<Mdl>>(a, src, xfree, gfree, stage_sm, lane, tm);
       }
     }
     tm.flush(a.ctl, lane);
@@ -1186,8 +1231,8 @@ static int check_problem(const crl_problem_t* p) {
 static int check_opts(const crl_solver_opts_t* o) {
     if (!o) return CRL_ERR_BAD_ARGUMENT;
     if (o->max_iter < 0 || o->max_line_search < 0 || o->reserved2 != 0) return CRL_ERR_BAD_ARGUMENT;
-    if (o->reserved != 0 && o->reserved != 2 && o->reserved != 12 && o->reserved != 20 && o->reserved != 21 && o->reserved != 22)
-        return CRL_ERR_BAD_ARGUMENT;
+    if (o->reserved != 0 && o->reserved != 2 && o->reserved != 12 && (o->reserved < 20 || o->reserved > 23))
+        return CRL_ERR_BAD_ARGUMENT;             // a configuration that is not compiled in is rejected when the grid is sized
     if (o->line_search_method < CRL_LS_VANILLA || o->line_search_method > CRL_LS_NONE) return CRL_ERR_BAD_ARGUMENT;
     if (o->stopping_method < CRL_STOP_RELATIVE || o->stopping_method > CRL_STOP_VANILLA) return CRL_ERR_BAD_ARGUMENT;
     return CRL_OK;
@@ -1229,7 +1274,7 @@ template <class Mdl, class R>
 static int coop_threshold_for(const crl_solver_opts_t* o, int T) {
     if (!CoopSupport<Mdl>::value || o->coop_threshold < 0) return -1;
     (void)T;
-    static_assert(!CoopSupport<Mdl>::value || coop_smem_reals<Mdl, kCoopNT>() <= 2 * StageLayout<Mdl, R>::STAGE,
+    static_assert(!CoopSupport<Mdl>::value || coop_smem_reals<Mdl, kCoopNTFor<Mdl>>() <= 2 * StageLayout<Mdl, R>::STAGE,
                   "the cooperative engine's shared-memory area must fit the warp's staging area");
     const int th = o->coop_threshold == 0 ? 12 : o->coop_threshold;
     return th > 32 ? 32 : th;
@@ -1272,7 +1317,8 @@ static unsigned blocks_for(long long work) { return (unsigned)((work + kBlock - 
 //   2      : lane-per-trajectory kernel, 4 warps per CTA, 2 resident CTAs per SM, warps free-running
 //   12     : the same, warps of a CTA phase-locked (SYNC) - the default
 //   20, 21 : the cooperative engine as the whole solve (coop_solve_kernel, 4 trajectories per warp), 2 / 3
-//            resident CTAs per SM (TwoLink / ThreeLink only); 22 (development builds): 2 trajectories per warp
+//            resident CTAs per SM; 22, 23 (development builds, -DCRL_DEV_FAST): 2 / 8 trajectories per warp
+//            (element-per-lane / pair-group backward pass)
 // Every configuration produces the same results bit for bit.
 template <class R> struct SolveCfg;
 template <> struct SolveCfg<double> { static constexpr int kDefault = 12; };
@@ -1335,9 +1381,10 @@ struct CoopVariant {
     switch (v) {                                                                   \
         case 2: { using V = SolveVariant<Mdl, R, 4, 2, false>; __VA_ARGS__; } break;  \
         case 12: { using V = SolveVariant<Mdl, R, 4, 2, true>; __VA_ARGS__; } break;  \
-        case 20: { CRL_COOP_VARIANT(4, 2, 4, __VA_ARGS__) } break;                       \
-        case 21: { CRL_COOP_VARIANT(4, 3, 4, __VA_ARGS__) } break;                       \
+        case 20: { CRL_COOP_VARIANT(4, 2, kCoopNTFor<Mdl>, __VA_ARGS__) } break;         \
+        case 21: { CRL_COOP_VARIANT(4, 3, kCoopNTFor<Mdl>, __VA_ARGS__) } break;         \
         case 22: { CRL_COOP_VARIANT(4, 2, 2, __VA_ARGS__) } break;                       \
+        case 23: { CRL_COOP_VARIANT(4, 2, 8, __VA_ARGS__) } break;                       \
         default: break;                                                            \
     }
 #else
@@ -1345,8 +1392,8 @@ struct CoopVariant {
     switch (v) {                                                                   \
         case 2: { using V = SolveVariant<Mdl, R, 4, 2, false>; __VA_ARGS__; } break;  \
         case 12: { using V = SolveVariant<Mdl, R, 4, 2, true>; __VA_ARGS__; } break;  \
-        case 20: { CRL_COOP_VARIANT(4, 2, 4, __VA_ARGS__) } break;                       \
-        case 21: { CRL_COOP_VARIANT(4, 3, 4, __VA_ARGS__) } break;                       \
+        case 20: { CRL_COOP_VARIANT(4, 2, kCoopNTFor<Mdl>, __VA_ARGS__) } break;         \
+        case 21: { CRL_COOP_VARIANT(4, 3, kCoopNTFor<Mdl>, __VA_ARGS__) } break;         \
         default: break;                                                            \
     }
 #endif

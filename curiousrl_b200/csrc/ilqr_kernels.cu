@@ -1408,6 +1408,19 @@ static void solve_config(int requested, int variant, int T, int* grid, int* warp
     CRL_SOLVE_VARIANT(v, (*grid = V::grid(requested), *warps = V::kWarps, *slot_elems = V::slot_elems(T)));
 }
 
+// Configuration used when the caller leaves the choice open (opts->reserved == 0): the lane-per-trajectory
+// kernel, unless the batch does not even fill its resident lanes once (kAutoCoopBatch = 148 SMs x 8 warps x
+// 32 lanes): such a solve is all tail, and the cooperative engine as the whole solve is 5 - 25 % faster
+// (measured, ThreeLink to convergence: 82 vs 105 ms at 1,024 trajectories, 152 vs 192 ms at 16,384, 210 vs
+// 231 ms at 32,768; 333 vs 318 ms at 65,536) and 6x faster per iteration for a single problem.
+constexpr long long kAutoCoopBatch = 148LL * 8 * 32;
+template <class Mdl, class R>
+static int effective_variant(const crl_problem_t* prob, const crl_solver_opts_t* opts) {
+    if (opts->reserved > 0) return opts->reserved;
+    if (CoopSupport<Mdl>::value && opts->coop_threshold >= 0 && prob->batch <= kAutoCoopBatch) return 20;
+    return SolveCfg<R>::kDefault;
+}
+
 template <class Mdl, class R>
 static void solve_launch(int variant, int grid, cudaStream_t s, const SolveArgs<R>& a) {
     const int v = variant > 0 ? variant : SolveCfg<R>::kDefault;
@@ -1576,7 +1589,8 @@ size_t crl_solve_workspace_bytes(const crl_problem_t* prob, const crl_solver_opt
     long long reals = 0;
     int grid = 0, warps = 0;
     CRL_DISPATCH(prob->model, prob->dtype,
-                 (solve_config<Mdl, R>(opts->grid_blocks, opts->reserved, prob->horizon, &grid, &warps, &reals)));
+                 (solve_config<Mdl, R>(opts->grid_blocks, effective_variant<Mdl, R>(prob, opts), prob->horizon, &grid, &warps,
+                                       &reals)));
     if (grid <= 0) return 0;
     const size_t elem = prob->dtype == CRL_F64 ? 8 : 4;
     const size_t slots = (size_t)grid * warps;
@@ -1605,7 +1619,8 @@ int crl_solve(const crl_problem_t* prob, const crl_solver_opts_t* opts, const vo
     int grid = 0, warps = 0;
     long long slot_elems = 0;
     CRL_DISPATCH(prob->model, prob->dtype,
-                 (solve_config<Mdl, R>(opts->grid_blocks, opts->reserved, prob->horizon, &grid, &warps, &slot_elems)));
+                 (solve_config<Mdl, R>(opts->grid_blocks, effective_variant<Mdl, R>(prob, opts), prob->horizon, &grid, &warps,
+                                       &slot_elems)));
     if (grid <= 0) return CRL_ERR_BAD_ARGUMENT;
     qbytes = queue_bytes((size_t)grid * warps);
     cudaError_t e = cudaMemsetAsync(workspace, 0, kCtlBytes + qbytes, s);   // counters and the queue's ready flags
@@ -1629,7 +1644,7 @@ int crl_solve(const crl_problem_t* prob, const crl_solver_opts_t* opts, const vo
         a.ws = (R*)((char*)workspace + kCtlBytes + qbytes);
         a.coop_threshold = coop_threshold_for<Mdl, R>(opts, prob->horizon);
         a.slot_elems = slot_elems;
-        solve_launch<Mdl, R>(opts->reserved, grid, s, a);
+        solve_launch<Mdl, R>(effective_variant<Mdl, R>(prob, opts), grid, s, a);
     });
     return cuda_status(cudaGetLastError());
 }

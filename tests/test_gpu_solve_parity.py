@@ -230,8 +230,10 @@ def test_every_scheduling_path_gives_the_same_bits(model, B, T):
     x0, tgt = synthetic_batch(model, B, seed=3)
     ref = make_algo(model, T, verify=False, coop_threshold=-1).solve_batch(x0, tgt, trace=True)
     assert int((ref.iterations > 50).sum()) > 0 or B < 100          # the batch does have a tail
-    for kw in (dict(), dict(coop_threshold=32), dict(coop_threshold=2), dict(occupancy=2), dict(occupancy=20),
-               dict(occupancy=21)):
+    # occupancy=0 picks the configuration by batch size (all-engine below the resident lane count), so the hybrid
+    # paths are asked for explicitly (12 = phase-locked lane kernel + cooperative tail)
+    for kw in (dict(), dict(occupancy=12), dict(occupancy=12, coop_threshold=32), dict(occupancy=12, coop_threshold=2),
+               dict(occupancy=2), dict(occupancy=2, coop_threshold=6), dict(occupancy=20), dict(occupancy=21)):
         res = make_algo(model, T, verify=False, **kw).solve_batch(x0, tgt, trace=True)
         for f in ("iterations", "converged", "obj_fun_value", "trajectory", "alpha_trace"):
             assert torch.equal(getattr(res, f), getattr(ref, f)), "%s differs with %s" % (f, kw)
@@ -249,7 +251,7 @@ def test_cooperative_paths_fixed_work_and_line_search_modes():
                dict(line_search_method="none", max_iter=15), dict(line_search_method="feasibility"),
                dict(stopping_method="vanilla", stopping_criterion=1e-3), dict(max_line_search=0, max_iter=5)):
         ref = make_algo(model, T, verify=False, coop_threshold=-1, **kw).solve_batch(x0, tgt, trace=True)
-        for extra in (dict(coop_threshold=32), dict(occupancy=21)):
+        for extra in (dict(), dict(occupancy=12, coop_threshold=32), dict(occupancy=21)):
             res = make_algo(model, T, verify=False, **kw, **extra).solve_batch(x0, tgt, trace=True)
             for f in ("iterations", "converged", "obj_fun_value", "trajectory", "alpha_trace"):
                 assert torch.equal(getattr(res, f), getattr(ref, f)), "%s differs with %s %s" % (f, kw, extra)
@@ -262,7 +264,7 @@ def test_scheduling_paths_at_tiny_horizons(model, T):
     from curiousrl_b200.utils.synthetic import synthetic_batch
     x0, tgt = synthetic_batch(model, 70, seed=11)
     ref = make_algo(model, T, verify=False, coop_threshold=-1, max_iter=30).solve_batch(x0, tgt, trace=True)
-    for kw in (dict(), dict(coop_threshold=32), dict(occupancy=20)):
+    for kw in (dict(), dict(occupancy=12), dict(occupancy=12, coop_threshold=32), dict(occupancy=20)):
         res = make_algo(model, T, verify=False, max_iter=30, **kw).solve_batch(x0, tgt, trace=True)
         for f in ("iterations", "converged", "obj_fun_value", "trajectory", "alpha_trace"):
             assert torch.equal(getattr(res, f), getattr(ref, f)), "%s differs with %s at T=%d" % (f, kw, T)

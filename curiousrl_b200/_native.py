@@ -11,8 +11,10 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int
 
 from . import build as _build
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MODEL_IDS = {"TwoLinkPlanarManipulator": 0, "ThreeLinkPlanarManipulator": 1, "RoboticArmTracking": 2}
+# the same scenarios under LogBarrieriLQR's cost (include/curiousrl_b200.h: CRL_*_BARRIER); FP64 only
+BARRIER_MODEL_IDS = {name: mid + 3 for name, mid in MODEL_IDS.items()}
 DTYPE_IDS = {"float64": 0, "float32": 1}
 LINE_SEARCH_IDS = {"vanilla": 0, "feasibility": 1, "none": 2}
 STOPPING_IDS = {"relative": 0, "vanilla": 1}

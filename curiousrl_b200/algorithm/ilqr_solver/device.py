@@ -39,7 +39,8 @@ class BatchResult:
 
 
 class DeviceModel:
-    def __init__(self, model_name: str, T: int, u_lo: float, u_hi: float, dtype: str = "float64", device=None):
+    def __init__(self, model_name: str, T: int, u_lo: float, u_hi: float, dtype: str = "float64", device=None,
+                 barrier: bool = False):
         if model_name not in _native.MODEL_IDS:
             raise Exception('Scenario "%s" has no device model in curiousrl_b200 (supported: %s); '
                             "there is no CPU fallback." % (model_name, ", ".join(_native.MODEL_IDS)))
@@ -49,7 +50,10 @@ class DeviceModel:
         if not torch.cuda.is_available():
             raise RuntimeError("curiousrl_b200 needs a CUDA device (B200); none is visible and there is no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.model_name, self.model_id = model_name, _native.MODEL_IDS[model_name]
+        if barrier and dtype != "float64":
+            raise ValueError("the log-barrier cost is compiled for float64 only")
+        self.model_name = model_name
+        self.model_id = (_native.BARRIER_MODEL_IDS if barrier else _native.MODEL_IDS)[model_name]
         self.n, self.m, self.p = _native.model_dims(self.model_id)
         self.d = self.n + self.m
         self.T = int(T)

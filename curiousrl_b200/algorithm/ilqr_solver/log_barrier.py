@@ -1,0 +1,214 @@
+"""LogBarrieriLQR with the reference's Python surface, executing on the B200.
+
+Reference: /root/reference/CuriousRL/algorithm/ilqr_solver/log_barrier_ilqr.py:13-156 - the solver
+Example/RoboticArmTrackingIteractive.py:11 uses.  Every finite bound of the scenario adds
+`(-1/t) log(-(lo - x_u[i]))` / `(-1/t) log(-(x_u[i] - hi))` to the running cost (:91-95), the barrier
+parameter t is appended to `add_param` as an extra column (:96-101), the line search is the
+"feasibility" one (:21) and `solve()` runs one inner iLQR loop per t in `t = [0.5, ..., 100]`, resetting
+the stored cost to +inf after each converged inner loop (:121-146).
+
+Device side: the same kernels as BasiciLQR, instantiated for the barrier cost (`Barrier<Model>` in
+csrc/ilqr_models.cuh, model ids CRL_*_BARRIER) - non-constant action entries of the cost gradient and
+Hessian inside the fused Riccati pass, `log` terms in every rollout's cost.  One inner loop = one
+`crl_solve` launch warm-started with the previous loop's actions.  FP64 only; the lane-per-trajectory
+kernel runs the whole solve (the cooperative tail engine is compiled for the plain costs only).
+
+Quirks kept:
+* the FIRST backward pass after t moves on still uses cost derivatives evaluated with the previous t
+  (the reference computes C, c in the forward pass, before the outer loop updates add_param): the device
+  parameter row carries that stale value as its last entry;
+* the first inner loop never writes t (`if j != self._t[0]`, :122), so a second `solve()` on the same
+  object starts with the t the previous solve ended on;
+* `get_obj_add_param()` returns the [T, p + 1] array whose last column is t.
+"""
+from __future__ import annotations
+
+import time as _time
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from ... import _native
+from ...utils.Logger import logger
+from .device import BatchResult, DeviceModel
+from .solver import iLQRDynamicModel, iLQRObjectiveFunction, iLQRWrapper, _np
+
+
+class _RealCostOwner:
+    """Parameter source of the barrier-free cost evaluator: the first p columns of the solver's add_param."""
+
+    def __init__(self, algo):
+        self._algo = algo
+
+    def _params_for(self, B: int) -> torch.Tensor:
+        dev = self._algo._real_dev
+        ap = np.asarray(self._algo._obj_fun._add_param, dtype=np.float64)[:, :dev.p]
+        return dev.real(ap).reshape(1, dev.T, dev.p)
+
+
+class LogBarrierBatchResult(BatchResult):
+    """BatchResult + `inner_iterations` [B, len(t)] (iterations of every inner loop) and `real_obj_fun_value` [B]
+    (the barrier-free cost of the final trajectories, what the reference reports, :138)."""
+    inner_iterations: Optional[torch.Tensor] = None
+    real_obj_fun_value: Optional[torch.Tensor] = None
+
+
+class LogBarrieriLQR(iLQRWrapper):
+    """Log-barrier iLQR (log_barrier_ilqr.py:13-156) on the GPU.  Constructor arguments as in the reference;
+    `device`, `verify`, `grid_blocks` as for BasiciLQR."""
+
+    def __init__(self, max_iter=1000, is_check_stop=True, stopping_criterion=1e-6, max_line_search=50, gamma=0.5,
+                 t=[0.5, 1., 2., 5., 10., 20., 50., 100.], line_search_method="feasibility", stopping_method="relative",
+                 device=None, verify=True, grid_blocks=0):
+        super().__init__(stopping_criterion=stopping_criterion, max_line_search=max_line_search, gamma=gamma,
+                         line_search_method=line_search_method, stopping_method=stopping_method,
+                         max_iter=max_iter, is_check_stop=is_check_stop)
+        self._t = list(t)
+        self._max_iter = max_iter
+        self._is_check_stop = is_check_stop
+        self._device = device
+        self._verify = verify
+        self._grid_blocks = grid_blocks
+        self._coop_threshold = -1            # barrier models run on the lane-per-trajectory kernel only
+        self._trajectory = None
+        self._t_stale = None                 # the t the next first backward pass still sees
+        self.last_result: Optional[BatchResult] = None
+        self.inner_iterations: List[int] = []
+
+    # ------------------------------------------------------------------ init
+    def init(self, scenario) -> "LogBarrieriLQR":
+        if not scenario.with_model() or scenario.is_action_discrete() or scenario.is_output_image():
+            raise Exception('Scenario "' + scenario.name + '" cannot learn with LogBarrieriLQR')
+        constr = np.asarray(scenario.constr, dtype=np.float64)
+        n = int(scenario.init_state.shape[0])
+        if not (np.all(constr[:n, 0] == -np.inf) and np.all(constr[:n, 1] == np.inf)):
+            raise Exception('Scenario "%s": finite state bounds are not supported by the device models' % scenario.name)
+        if scenario.name not in _native.MODEL_IDS:
+            raise Exception('Scenario "%s" has no device model in curiousrl_b200; there is no CPU fallback.' % scenario.name)
+        lo, hi = _native.model_default_bounds(_native.MODEL_IDS[scenario.name])
+        if not (np.all(constr[n:, 0] == lo) and np.all(constr[n:, 1] == hi)):
+            raise Exception('Scenario "%s": the barrier cost is compiled for the action box [%g, %g]' % (scenario.name, lo, hi))
+        T = int(scenario.init_action.shape[0])
+        self._dev = DeviceModel(scenario.name, T, lo, hi, device=self._device, barrier=True)
+        self._real_dev = DeviceModel(scenario.name, T, lo, hi, device=self._device)
+        self._dynamic_model = iLQRDynamicModel(self._dev, scenario.init_state, scenario.init_action, self)
+        if scenario.add_param is None:
+            raise Exception('Scenario "%s" has no add_param (target)' % scenario.name)
+        add_param = np.hstack([np.asarray(scenario.add_param, dtype=np.float64), self._t[0] * np.ones((T, 1))])   # :100-101
+        self._obj_fun = iLQRObjectiveFunction(self._dev, add_param, self)
+        self._real_obj_fun = iLQRObjectiveFunction(self._real_dev, None, _RealCostOwner(self))
+        self._t_stale = None
+        if self._verify:
+            self._verify_against(scenario)
+        return self
+
+    def _verify_against(self, scenario):
+        """The barrier cost of the device model against the scenario's own symbolic cost + barrier terms."""
+        import sympy as sp
+        dev, rng = self._dev, np.random.default_rng(4321)
+        xu, t_var = scenario.x_u_var, sp.symbols("t")
+        expr = scenario.obj_fun
+        for i, c in enumerate(np.asarray(scenario.constr, dtype=np.float64)):
+            if not np.isinf(c[0]):
+                expr = expr + (-1 / t_var) * sp.log(-(c[0] - xu[i]))
+            if not np.isinf(c[1]):
+                expr = expr + (-1 / t_var) * sp.log(-(xu[i] - c[1]))
+        l = sp.lambdify([xu, (*scenario.add_param_var, t_var)], expr, "math")
+        for _ in range(3):
+            X = rng.uniform(-2.0, 2.0, (1, dev.T, dev.d))
+            X[:, :, dev.n:] = rng.uniform(0.9 * dev.u_lo, 0.9 * dev.u_hi, (1, dev.T, dev.m))
+            prm = np.concatenate([rng.uniform(-3.0, 3.0, dev.p - 2), [rng.uniform(0.5, 100.0)], [1.0]])
+            J = float(dev.cost(X, dev.real(prm)).item())
+            J_ref = sum(float(l(X[0, t], prm[:-1])) for t in range(dev.T))
+            if not np.isclose(J, J_ref, rtol=1e-9):
+                raise Exception('Scenario "%s": obj_fun + barrier differs from the device model' % scenario.name)
+
+    # ------------------------------------------------------------------ parameters
+    def _params_for(self, B: int) -> torch.Tensor:
+        """Device parameter rows [1, T, p]: the reference's add_param (targets, t) + the stale t of the next first
+        backward pass (= t unless an outer loop just moved it)."""
+        ap = np.asarray(self._obj_fun._add_param, dtype=np.float64)
+        stale = ap[:, -1:] if self._t_stale is None else np.full((ap.shape[0], 1), float(self._t_stale))
+        return self._dev.real(np.hstack([ap, stale])).reshape(1, self._dev.T, self._dev.p)
+
+    # ------------------------------------------------------------------ solve (B = 1, reference semantics)
+    def solve(self):
+        """One inner iLQR loop per barrier parameter (log_barrier_ilqr.py:104-149).  Returns None; results are left
+        in `_trajectory`, `inner_iterations` and the logger's JSON channel."""
+        dev = self._dev
+        start = _time.time()
+        x0 = np.asarray(self._dynamic_model._init_state, dtype=np.float64).reshape(1, dev.n)
+        U = np.asarray(self._dynamic_model._init_action, dtype=np.float64).reshape(dev.T, dev.m)
+        X0 = self._dynamic_model.eval_traj()
+        logger.info("[+ +] Initial Obj.Val.: %.5e" % self._real_obj_fun.eval_obj_fun(X0))
+        self.inner_iterations = []
+        total = -1
+        res = None
+        for j in self._t:
+            self._t_stale = None
+            if j != self._t[0]:                                      # :122-125
+                add_param = self.get_obj_add_param()
+                self._t_stale = float(add_param[0, -1])              # what C, c were evaluated with
+                add_param[:, -1] = j * np.ones((dev.T))
+                self.set_obj_add_param(add_param)
+            res = dev.solve(self._opts(self._max_iter, self._is_check_stop), x0, self._params_for(1), u0=U,
+                            J_init=np.asarray([self._obj_fun_value_last], dtype=np.float64), trace=True)
+            host = res.to_host()
+            iters = int(host.iterations[0])
+            for i in range(iters):
+                total += 1
+                logger.info("[+ +] Total Iter.No.%3d   Iter.No.%3d   Barrier Obj.Val.:%.5e" % (total, i, host.obj_fun_trace[0, i]))
+            traj = host.trajectory[0].astype(np.float64)
+            U = traj[:, dev.n:]
+            self._trajectory = traj[:, :, None]
+            self.inner_iterations.append(iters)
+            self._obj_fun_value_last = float(host.obj_fun_value[0])
+            logger.info("[+ +] Obj.Val.:%.5e" % self._real_obj_fun.eval_obj_fun(self._trajectory))
+            logger.save_to_json(trajectory=self._trajectory.tolist())
+            if bool(host.converged[0]) and self._is_check_stop:       # :140-146
+                self.set_obj_fun_value(np.inf)
+                logger.info("[+ +] Complete One Inner Loop! The log barrier parameter t is %.5f" % j + " in this iteration!")
+        self._t_stale = None
+        self.last_result = res
+        logger.info("[+ +] Completed! All Time:%.5e" % (_time.time() - start))
+
+    # ------------------------------------------------------------------ batched extension
+    def solve_batch(self, init_state, add_param=None, init_action=None, return_trajectory=True) -> LogBarrierBatchResult:
+        """B independent problems: one `crl_solve` launch per barrier parameter, every launch warm-started with the
+        previous one's actions.  init_state [B, n]; add_param [B, p] constant targets (None = the scenario's);
+        init_action None (the scenario's), [T, m] or [B, T, m].  Fresh problems: the stored cost starts at +inf."""
+        dev, rdev = self._dev, self._real_dev
+        x0 = dev.real(init_state).reshape(-1, dev.n)
+        B = x0.shape[0]
+        if add_param is None:
+            tgt = dev.real(np.asarray(self._obj_fun._add_param, dtype=np.float64)[0, :rdev.p]).reshape(1, rdev.p).expand(B, rdev.p)
+        else:
+            tgt = dev.real(add_param).reshape(B, rdev.p)
+        prm = torch.empty((B, dev.p), device=dev.device, dtype=dev.dtype)
+        prm[:, :rdev.p] = tgt
+        u0 = self._dynamic_model._init_action if init_action is None else init_action
+        if isinstance(u0, np.ndarray) and not u0.any():
+            u0 = None
+        J_init = torch.full((B,), float("inf"), dtype=torch.float64, device=dev.device)
+        inner = torch.zeros((B, len(self._t)), dtype=torch.int32, device=dev.device)
+        opts = self._opts(self._max_iter, self._is_check_stop)
+        res = None
+        t_prev = self._t[0]
+        for s, t in enumerate(self._t):
+            prm[:, rdev.p] = t
+            prm[:, rdev.p + 1] = t_prev
+            res = dev.solve(opts, x0, prm, u0=u0, J_init=J_init, return_trajectory=True)
+            inner[:, s] = res.iterations
+            u0 = res.trajectory[:, :, dev.n:].contiguous()
+            if self._is_check_stop:
+                J_init = torch.where(res.converged.bool(), torch.full_like(res.obj_fun_value, float("inf")), res.obj_fun_value)
+            else:
+                J_init = res.obj_fun_value.clone()
+            t_prev = t
+        out = LogBarrierBatchResult(res.trajectory if return_trajectory else None, res.obj_fun_value, inner.sum(dim=1).to(torch.int32),
+                                    res.converged)
+        out.inner_iterations = inner
+        out.real_obj_fun_value = rdev.cost(res.trajectory, tgt.contiguous())
+        self.last_result = out
+        return out

@@ -399,7 +399,7 @@ CRL_HD void riccati_step(const R* xu, const R* p, ValueFn<Mdl, R>& vf, R (&Kout)
         CRL_UNROLL for (int b = 0; b < M; ++b) {
             R acc = R(0); bool have = false;
             CRL_UNROLL for (int k = 0; k < NS; ++k) acc_kind(acc, have, MB[a][k], Mdl::bkind(k, b), Mdl::bconst(k, b), B[k][b]);
-            Quu[a][b] = (a == b) ? R(cost_hess<Mdl>(N + a)) + acc : acc;
+            Quu[a][b] = (a == b) ? cost_hess_u<Mdl, R>(a, xu[N + a], p) + acc : acc;
         }
     }
     // q = c + F^T v
@@ -481,9 +481,11 @@ struct DirectRowFeed {                       // rows of a stored trajectory, las
     }
 };
 
+// `first` (barrier models only): this is the first backward pass of a solve - its cost derivatives use
+// the stale barrier parameter p[kT + 1] (see Barrier in ilqr_models.cuh).
 template <class Mdl, class R, int KN, class RowFeed, int SCK>
 CRL_HD void backward_fused_f(RowFeed& rows, const ParamRef<R>& prm, int T, View<R, Mdl::M * KN, SCK> Kv,
-                             View<R, Mdl::M, SCK> kv) {
+                             View<R, Mdl::M, SCK> kv, bool first = false) {
     constexpr int NS = Mdl::NS, M = Mdl::M, D = Mdl::D, P = Mdl::P;
     ValueFn<Mdl, R> vf;
     vf.clear();
@@ -492,6 +494,9 @@ CRL_HD void backward_fused_f(RowFeed& rows, const ParamRef<R>& prm, int T, View<
         R xu[D], p[P], Kt[M][NS], kt[M];
         rows.get(T - 1 - t, xu);
         CRL_UNROLL for (int i = 0; i < P; ++i) p[i] = prm.get(t, i);
+        if constexpr (Mdl::kBarrier) {
+            if (first) p[Mdl::kT] = p[Mdl::kT + 1];
+        }
         riccati_step<Mdl, R>(xu, p, vf, Kt, kt);
         R* Kr = Kv.row(t);
         R* kr = kv.row(t);
@@ -533,7 +538,7 @@ CRL_HD void derivs_dense(const R* xu, const R* p, R* F, R* c, R* C) {
     for (int i = 0; i < D * D; ++i) C[i] = R(0);
     CRL_UNROLL for (int i = 0; i < D; ++i) {
         c[i] = cost_grad<Mdl, R>(i, xu[i], p);
-        C[i * D + i] = R(cost_hess<Mdl>(i));
+        C[i * D + i] = i >= N ? cost_hess_u<Mdl, R>(i - N, xu[i], p) : R(cost_hess<Mdl>(i));
     }
 }
 

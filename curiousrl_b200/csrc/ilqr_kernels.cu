@@ -939,7 +939,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) solve_kernel(SolveArgs<R> a)
         const unsigned act_mask = __ballot_sync(kFull, active);
         if (active) {
             TileRowFeed<Mdl, R> rows(act_mask, Xc.base - lane, stage_sm, stage_bar);
-            backward_fused_f<Mdl, R, NS>(rows, prm, T, Kv, kv);
+            backward_fused_f<Mdl, R, NS>(rows, prm, T, Kv, kv, it == 0);
         }
 #ifndef CRL_NO_MID_BARRIER
         if (SYNC) __syncthreads();
@@ -1218,11 +1218,12 @@ static OptsDev to_dev(const crl_solver_opts_t* o) {
 
 static int check_problem(const crl_problem_t* p) {
     if (!p) return CRL_ERR_BAD_ARGUMENT;
-    if (p->model < CRL_TWO_LINK || p->model > CRL_ROBOTIC_ARM) return CRL_ERR_UNSUPPORTED_MODEL;
+    if (p->model < CRL_TWO_LINK || p->model > CRL_ROBOTIC_ARM_BARRIER) return CRL_ERR_UNSUPPORTED_MODEL;
     if (p->dtype != CRL_F64 && p->dtype != CRL_F32) return CRL_ERR_BAD_ARGUMENT;
+    if (p->model >= CRL_TWO_LINK_BARRIER && p->dtype != CRL_F64) return CRL_ERR_UNSUPPORTED_MODEL;   // barrier models: FP64 only
     if (p->batch < 0 || p->horizon < 1) return CRL_ERR_BAD_ARGUMENT;
     if (p->batch > 0 && !p->params) return CRL_ERR_BAD_ARGUMENT;
-    if (p->params_stride_t != 0 && p->params_stride_t != 2) return CRL_ERR_BAD_ARGUMENT;
+    if (p->params_stride_t != 0 && p->params_stride_t != (p->model >= CRL_TWO_LINK_BARRIER ? 4 : 2)) return CRL_ERR_BAD_ARGUMENT;
     if (p->params_stride_b < 0) return CRL_ERR_BAD_ARGUMENT;
     if (!(p->u_lo <= p->u_hi)) return CRL_ERR_BAD_ARGUMENT;
     return CRL_OK;
@@ -1290,6 +1291,10 @@ static unsigned blocks_for(long long work) { return (unsigned)((work + kBlock - 
             using R = double;                                                            \
             using Mdl = ThreeLink;                                                       \
             __VA_ARGS__;                                                                 \
+        } else if ((dtype) == CRL_F64 && (model) == CRL_THREE_LINK_BARRIER) {            \
+            using R = double;                                                            \
+            using Mdl = Barrier<ThreeLink>;                                              \
+            __VA_ARGS__;                                                                 \
         }                                                                                \
     } while (0)
 #else
@@ -1301,6 +1306,9 @@ static unsigned blocks_for(long long work) { return (unsigned)((work + kBlock - 
                 case CRL_TWO_LINK: { using Mdl = TwoLink; __VA_ARGS__; } break;                 \
                 case CRL_THREE_LINK: { using Mdl = ThreeLink; __VA_ARGS__; } break;             \
                 case CRL_ROBOTIC_ARM: { using Mdl = RoboticArm; __VA_ARGS__; } break;           \
+                case CRL_TWO_LINK_BARRIER: { using Mdl = Barrier<TwoLink>; __VA_ARGS__; } break;        \
+                case CRL_THREE_LINK_BARRIER: { using Mdl = Barrier<ThreeLink>; __VA_ARGS__; } break;    \
+                case CRL_ROBOTIC_ARM_BARRIER: { using Mdl = Barrier<RoboticArm>; __VA_ARGS__; } break;  \
             }                                                                            \
         } else {                                                                         \
             using R = float;                                                             \
@@ -1379,7 +1387,7 @@ struct CoopVariant {
 #ifdef CRL_DEV_FAST
 #define CRL_SOLVE_VARIANT(v, ...)                                                  \
     switch (v) {                                                                   \
-        case 2: { using V = SolveVariant<Mdl, R, 4, 2, false>; __VA_ARGS__; } break;  \
+        case 2: if constexpr (!Mdl::kBarrier) { using V = SolveVariant<Mdl, R, 4, 2, false>; __VA_ARGS__; } break;  \
         case 12: { using V = SolveVariant<Mdl, R, 4, 2, true>; __VA_ARGS__; } break;  \
         case 20: { CRL_COOP_VARIANT(4, 2, kCoopNTFor<Mdl>, __VA_ARGS__) } break;         \
         case 21: { CRL_COOP_VARIANT(4, 3, kCoopNTFor<Mdl>, __VA_ARGS__) } break;         \
@@ -1390,7 +1398,7 @@ struct CoopVariant {
 #else
 #define CRL_SOLVE_VARIANT(v, ...)                                                  \
     switch (v) {                                                                   \
-        case 2: { using V = SolveVariant<Mdl, R, 4, 2, false>; __VA_ARGS__; } break;  \
+        case 2: if constexpr (!Mdl::kBarrier) { using V = SolveVariant<Mdl, R, 4, 2, false>; __VA_ARGS__; } break;  \
         case 12: { using V = SolveVariant<Mdl, R, 4, 2, true>; __VA_ARGS__; } break;  \
         case 20: { CRL_COOP_VARIANT(4, 2, kCoopNTFor<Mdl>, __VA_ARGS__) } break;         \
         case 21: { CRL_COOP_VARIANT(4, 3, kCoopNTFor<Mdl>, __VA_ARGS__) } break;         \
@@ -1454,6 +1462,9 @@ int crl_model_dims(int model, int* n, int* m, int* p) {
         case CRL_TWO_LINK: N = TwoLink::N; M = TwoLink::M; P = TwoLink::P; break;
         case CRL_THREE_LINK: N = ThreeLink::N; M = ThreeLink::M; P = ThreeLink::P; break;
         case CRL_ROBOTIC_ARM: N = RoboticArm::N; M = RoboticArm::M; P = RoboticArm::P; break;
+        case CRL_TWO_LINK_BARRIER: N = TwoLink::N; M = TwoLink::M; P = Barrier<TwoLink>::P; break;
+        case CRL_THREE_LINK_BARRIER: N = ThreeLink::N; M = ThreeLink::M; P = Barrier<ThreeLink>::P; break;
+        case CRL_ROBOTIC_ARM_BARRIER: N = RoboticArm::N; M = RoboticArm::M; P = Barrier<RoboticArm>::P; break;
         default: return CRL_ERR_UNSUPPORTED_MODEL;
     }
     if (n) *n = N;
@@ -1465,9 +1476,9 @@ int crl_model_dims(int model, int* n, int* m, int* p) {
 int crl_model_default_bounds(int model, double* u_lo, double* u_hi) {
     double lo, hi;
     switch (model) {
-        case CRL_TWO_LINK: lo = TwoLink::u_lo(0); hi = TwoLink::u_hi(0); break;
-        case CRL_THREE_LINK: lo = ThreeLink::u_lo(0); hi = ThreeLink::u_hi(0); break;
-        case CRL_ROBOTIC_ARM: lo = RoboticArm::u_lo(0); hi = RoboticArm::u_hi(0); break;
+        case CRL_TWO_LINK: case CRL_TWO_LINK_BARRIER: lo = TwoLink::u_lo(0); hi = TwoLink::u_hi(0); break;
+        case CRL_THREE_LINK: case CRL_THREE_LINK_BARRIER: lo = ThreeLink::u_lo(0); hi = ThreeLink::u_hi(0); break;
+        case CRL_ROBOTIC_ARM: case CRL_ROBOTIC_ARM_BARRIER: lo = RoboticArm::u_lo(0); hi = RoboticArm::u_hi(0); break;
         default: return CRL_ERR_UNSUPPORTED_MODEL;
     }
     if (u_lo) *u_lo = lo;

@@ -35,6 +35,9 @@ constexpr double kH = 0.01;
 template <int J>
 struct KinematicArm {
     static constexpr int NS = 2 * J, NO = 2, N = NS + NO, M = J, D = N + M, P = 2;
+    static constexpr bool kBarrier = false;
+    // order in which sympy prints the per-action terms of a sum (symbol names sort as strings: x_u10 < x_u8 < x_u9)
+    CRL_HD static constexpr int action_order(int k) { return J == 3 ? (k == 0 ? 2 : k - 1) : k; }
 
     CRL_HD static constexpr int akind(int i, int j) { return i == j ? K1 : ((i % 2 == 0 && j == i + 1) ? KC : KZ); }
     CRL_HD static constexpr double aconst(int, int) { return kH; }
@@ -160,6 +163,8 @@ struct ThreeLink : KinematicArm<3> {
 struct RoboticArm {
     static constexpr int ID = 2;
     static constexpr int NS = 4, NO = 2, N = 6, M = 2, D = 8, P = 2;
+    static constexpr bool kBarrier = false;
+    CRL_HD static constexpr int action_order(int k) { return k; }
     static constexpr double k1 = 0.0266666666666667, k2 = 0.0233333333333333, kden = 6.22222222222222;
 
     CRL_HD static constexpr int akind(int i, int j) {
@@ -271,17 +276,69 @@ struct RoboticArm {
     }
 };
 
+// ---- log-barrier variant of a model (LogBarrieriLQR, log_barrier_ilqr.py:86-101) -----------
+// Every finite bound of the scenario adds  (-1/t) log(-(lo - u_a))  /  (-1/t) log(-(u_a - hi))  to the
+// running cost (in the three arm scenarios only the actions are bounded).  As in the reference the
+// barrier parameter t rides in the cost-parameter row: p = (target_x, target_y, t, t0), where t0 is
+// the t the reference's FIRST backward pass of a solve still sees - its C, c were evaluated by the
+// previous forward pass, before the outer loop moved t on (log_barrier_ilqr.py:121-131).
+// Expression forms as sympy prints them for the reference's lambdified cost / gradient / Hessian:
+//   l    = l_base - log(hi - u)/t ... - log(u + (-lo))/t ...        (all upper bounds first, actions in
+//                                                                    printed order)
+//   l_u  = 2 w u - 1/(t (u + (-lo))) + 1/(t (hi - u))
+//   l_uu = 2 w + 1/(t (u + (-lo))**2) + 1/(t (hi - u)**2)   (+ 1e-100)
+template <class Base>
+struct Barrier : Base {
+    static constexpr bool kBarrier = true;
+    static constexpr int ID = Base::ID + 3;
+    static constexpr int P = Base::P + 2;
+    static constexpr int kT = Base::P;                       // index of t in the parameter row; t0 follows
+    CRL_HD static double cost(const double* x, const double* p) {
+        double J = Base::cost(x, p);
+        const double t = p[kT];
+        CRL_UNROLL for (int k = 0; k < Base::M; ++k) {
+            const int a = Base::action_order(k);
+            J = J - ::log(Base::u_hi(a) - x[Base::N + a]) / t;
+        }
+        CRL_UNROLL for (int k = 0; k < Base::M; ++k) {
+            const int a = Base::action_order(k);
+            J = J - ::log(x[Base::N + a] + (-Base::u_lo(a))) / t;
+        }
+        return J;
+    }
+};
+
 // ---- cost derivatives shared by all three (diagonal quadratic tracking cost) -------------
 // grad_i = 2 w_i x_i                       for untargeted entries (printed as 20.0*x, 2.0*x, 0.02*x, or 0)
 // grad_i = -2 w_i p + 2 w_i x_i            for the two end-effector entries (printed -20000.0*p0 + 20000.0*x)
 // hess_ii = 2 w_i + 1e-100                 (ilqr_obj_fun.py:51: "+1e-100*eye" keeps every entry float)
+// Barrier models add the barrier terms to the action entries (p[kT] = t).
 template <class Mdl, class R>
 CRL_HD R cost_grad(int i, R xi, const R* p) {
     const R w2 = R(2.0 * Mdl::weight(i));
     if (i >= Mdl::NS && i < Mdl::N) return (-w2) * p[i - Mdl::NS] + w2 * xi;
+    if constexpr (Mdl::kBarrier) {
+        if (i >= Mdl::N) {
+            const int a = i - Mdl::N;
+            const R t = p[Mdl::kT];
+            return (w2 * xi - R(1) / (t * (xi + R(-Mdl::u_lo(a))))) + R(1) / (t * (R(Mdl::u_hi(a)) - xi));
+        }
+    }
     return (Mdl::weight(i) == 0.0) ? R(0.0) : w2 * xi;
 }
 template <class Mdl>
 CRL_HD constexpr double cost_hess(int i) { return 2.0 * Mdl::weight(i) + 1e-100; }
+// Hessian entry of action a: a constant for the plain models
+template <class Mdl, class R>
+CRL_HD R cost_hess_u(int a, R u, const R* p) {
+    if constexpr (Mdl::kBarrier) {
+        const R t = p[Mdl::kT];
+        const R lo = u + R(-Mdl::u_lo(a)), hi = R(Mdl::u_hi(a)) - u;
+        return ((R(2.0 * Mdl::weight(Mdl::N + a)) + R(1) / (t * (lo * lo))) + R(1) / (t * (hi * hi))) + R(1e-100);
+    } else {
+        (void)u; (void)p;
+        return R(cost_hess<Mdl>(Mdl::N + a));
+    }
+}
 
 }  // namespace crl

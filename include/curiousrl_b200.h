@@ -27,14 +27,21 @@
 extern "C" {
 #endif
 
-#define CRL_ABI_VERSION 2
+#define CRL_ABI_VERSION 3
 
 typedef void* crl_stream_t; /* cudaStream_t */
 
 enum crl_model {              /* scenario.name -> precompiled device model                     */
     CRL_TWO_LINK = 0,         /* TwoLinkPlanarManipulator   two_link_planar_manipulator.py:14  */
     CRL_THREE_LINK = 1,       /* ThreeLinkPlanarManipulator three_link_planar_manipulator.py:15 */
-    CRL_ROBOTIC_ARM = 2       /* RoboticArmTracking         robotic_arm_tracking.py:15         */
+    CRL_ROBOTIC_ARM = 2,      /* RoboticArmTracking         robotic_arm_tracking.py:15         */
+    /* The same scenarios under LogBarrieriLQR's cost (log_barrier_ilqr.py:86-101): every bounded action adds
+       (-1/t) log(-(lo - u)) + (-1/t) log(-(u - hi)).  FP64 only.  The parameter row grows to p = 4:
+       (target_x, target_y, t, t0), t0 = the barrier parameter the first backward pass of a solve still
+       sees (the reference evaluates its cost derivatives before the outer loop moves t on).            */
+    CRL_TWO_LINK_BARRIER = 3,
+    CRL_THREE_LINK_BARRIER = 4,
+    CRL_ROBOTIC_ARM_BARRIER = 5
 };
 enum crl_dtype { CRL_F64 = 0, CRL_F32 = 1 };
 enum crl_line_search { CRL_LS_VANILLA = 0, CRL_LS_FEASIBILITY = 1, CRL_LS_NONE = 2 }; /* ilqr_wrapper.py:74-146 */

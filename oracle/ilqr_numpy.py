@@ -17,6 +17,9 @@ It restates, function by function, what the reference computes on the path
 * `line_search`           first improving alpha = 1, g, g^2, ...               (ilqr_wrapper.py:74-146)
 * `is_stop`               relative / vanilla stopping tests                    (ilqr_wrapper.py:148-174)
 * `solve`                 outer loop of BasiciLQR.solve                        (basic_ilqr.py:68-97)
+* `BarrierScenario`       LogBarrieriLQR's cost: obj_fun + (-1/t) log terms, t appended to add_param
+                          (log_barrier_ilqr.py:84-101)
+* `solve_log_barrier`     LogBarrieriLQR.solve: one inner loop per barrier parameter  (log_barrier_ilqr.py:104-149)
 
 The arithmetic substrate is the reference's own: the same sympy expressions go
 through `sympy.lambdify` (printers "math" for the dynamics, "numpy" for the
@@ -267,3 +270,69 @@ def solve(prob: Problem, x0=None, target=None, U0=None, max_iter=1000, is_check_
             break
     return dict(X=X, J=J_last, J0=J0, iters=iters, Js=np.asarray(Js), alphas=np.asarray(alphas, dtype=np.int32),
                 rollouts=rollouts, stopped=stopped)
+
+
+# ----------------------------------------------------------------------------- LogBarrieriLQR
+
+class BarrierScenario:
+    """The scenario LogBarrieriLQR.init builds its barrier objective from (log_barrier_ilqr.py:84-101):
+    every finite bound adds (-1/t) log(-(lo - x_u[i])) / (-1/t) log(-(x_u[i] - hi)); the barrier parameter
+    t becomes the last add_param column, initialised with t0."""
+
+    def __init__(self, scenario, t0):
+        xu = scenario.x_u_var
+        t_var = sp.symbols("t")
+        constr = np.asarray(scenario.constr, dtype=np.float64)
+        obj = scenario.obj_fun
+        for i, c in enumerate(constr):
+            if not np.isinf(c[0]):
+                obj = obj + (-1 / t_var) * sp.log(-(c[0] - xu[i]))
+            if not np.isinf(c[1]):
+                obj = obj + (-1 / t_var) * sp.log(-(xu[i] - c[1]))
+        self.name = scenario.name
+        self.x_u_var = xu
+        self.init_state = scenario.init_state
+        self.init_action = scenario.init_action
+        self.constr = scenario.constr
+        self.dynamic_function = scenario.dynamic_function
+        self.obj_fun = obj
+        self.add_param_var = (*scenario.add_param_var, t_var)
+        T = int(scenario.init_action.shape[0])
+        self.add_param = np.hstack([np.asarray(scenario.add_param, dtype=np.float64), t0 * np.ones((T, 1))])
+
+
+def solve_log_barrier(prob_barrier: Problem, prob_real: Problem, x0=None, target=None, t_list=(0.5, 1., 2., 5., 10., 20., 50., 100.),
+                      max_iter=1000, is_check_stop=True, stopping_criterion=1e-6, max_line_search=10, gamma=0.5,
+                      line_search_method="feasibility", stopping_method="relative"):
+    """LogBarrieriLQR.solve (log_barrier_ilqr.py:104-149) for a fresh solver object.  `prob_barrier` is the
+    Problem of a BarrierScenario, `prob_real` the plain one (reported cost).  Note the order of operations the
+    reference has: C, c, F are evaluated inside the forward pass, so the first backward pass after t moves on
+    still sees derivatives taken with the previous t."""
+    T = prob_barrier.T
+    P_real = prob_real.params(target)
+    P = np.hstack([P_real, t_list[0] * np.ones((T, 1))])
+    X = rollout(prob_barrier, x0, None)
+    Fm, c, C = derivs(prob_barrier, X, P)
+    J_last = np.inf
+    inner, Js, Jreal, alphas = [], [], [], []
+    for j in t_list:
+        if j != t_list[0]:
+            P = P.copy()
+            P[:, -1] = j
+        n_it = 0
+        for _ in range(max_iter):
+            K, k = backward(prob_barrier, Fm, c, C)
+            X, J, a_idx, _n, _tried = line_search(prob_barrier, X, K, k, J_last, P, max_line_search, gamma, line_search_method)
+            stop = is_stop(J, J_last, stopping_criterion, stopping_method)
+            Fm, c, C = derivs(prob_barrier, X, P)
+            J_last = J
+            Js.append(J)
+            Jreal.append(cost(prob_real, X, P_real))
+            alphas.append(a_idx)
+            n_it += 1
+            if stop and is_check_stop:
+                J_last = np.inf
+                break
+        inner.append(n_it)
+    return dict(X=X, Jreal=Jreal[-1], inner_iters=np.asarray(inner), Js=np.asarray(Js), Jreals=np.asarray(Jreal),
+                alphas=np.asarray(alphas, dtype=np.int32))

@@ -111,3 +111,19 @@ def test_scheduling_options_reach_the_c_abi_struct():
     assert sig["coop_threshold"].default == 0 and sig["occupancy"].default == 0
     o = BasiciLQR(max_line_search=10, coop_threshold=-1, occupancy=20)._opts(max_iter=7, is_check_stop=False)
     assert (o.max_iter, o.is_check_stop, o.max_line_search, o.reserved, o.coop_threshold, o.reserved2) == (7, 0, 10, 20, -1, 0)
+
+
+def test_log_barrier_constructor_matches_reference():
+    """LogBarrieriLQR keeps the reference's constructor (log_barrier_ilqr.py:14-22) - same names, order and defaults."""
+    import inspect
+    from curiousrl_b200.algorithm.ilqr_solver import LogBarrieriLQR
+    sig = inspect.signature(LogBarrieriLQR.__init__).parameters
+    names = list(sig)[1:9]
+    assert names == ["max_iter", "is_check_stop", "stopping_criterion", "max_line_search", "gamma", "t", "line_search_method",
+                     "stopping_method"]
+    assert sig["max_iter"].default == 1000 and sig["max_line_search"].default == 50 and sig["gamma"].default == 0.5
+    assert sig["t"].default == [0.5, 1., 2., 5., 10., 20., 50., 100.]
+    assert sig["line_search_method"].default == "feasibility" and sig["stopping_method"].default == "relative"
+    for name in ("init", "solve", "forward_pass", "backward_pass", "set_init_state", "set_obj_add_param", "get_obj_add_param",
+                 "set_obj_fun_value", "get_obj_fun_value", "solve_batch"):
+        assert callable(getattr(LogBarrieriLQR, name))

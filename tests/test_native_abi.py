@@ -24,13 +24,16 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), "symbol %s declared in the header is not exported" % name
     assert sorted(_native.EXPORTS) == names
-    assert lib.crl_abi_version() == _native.ABI_VERSION == 2
+    assert lib.crl_abi_version() == _native.ABI_VERSION == 3
 
 
 def test_model_tables_and_status_strings():
     from curiousrl_b200 import _native
     assert _native.model_dims(0) == (6, 2, 2) and _native.model_dims(1) == (8, 3, 2) and _native.model_dims(2) == (6, 2, 2)
     assert _native.model_default_bounds(1) == (-100.0, 100.0) and _native.model_default_bounds(2) == (-500.0, 500.0)
+    # LogBarrieriLQR's variants of the three models: same sizes, parameter row (target_x, target_y, t, t0)
+    assert _native.model_dims(3) == (6, 2, 4) and _native.model_dims(4) == (8, 3, 4) and _native.model_dims(5) == (6, 2, 4)
+    assert _native.model_default_bounds(5) == (-500.0, 500.0)
     lib = _native.load()
     assert lib.crl_model_dims(7, None, None, None) == -2
     assert b"unsupported model" in lib.crl_status_string(-2)
@@ -55,7 +58,8 @@ def test_argument_validation_happens_before_any_cuda_call():
     opts = _native.SolverOpts(10, 1, 1e-6, 10, 0.5, 0, 0, 0, 0, 0, 0)
     dummy = ctypes.c_void_p(0x1000)
     assert lib.crl_rollout(None, dummy, None, 0, dummy, None, None) == -1
-    assert lib.crl_rollout(prob(model=5), dummy, None, 0, dummy, None, None) == -2
+    assert lib.crl_rollout(prob(model=6), dummy, None, 0, dummy, None, None) == -2
+    assert lib.crl_rollout(prob(model=5, dtype=1), dummy, None, 0, dummy, None, None) == -2   # barrier models are FP64 only
     assert lib.crl_rollout(prob(dtype=3), dummy, None, 0, dummy, None, None) == -1
     assert lib.crl_rollout(prob(horizon=0), dummy, None, 0, dummy, None, None) == -1
     assert lib.crl_rollout(prob(batch=-1), dummy, None, 0, dummy, None, None) == -1

@@ -92,3 +92,47 @@ def test_seeded_batch_end_to_end(golden, tag):
         assert r["J"] == float(g["batch_J"][b])
         assert np.array_equal(r["X"], g["batch_X"][b])
         assert np.array_equal(r["alphas"], g["batch_alphas"][b][:r["iters"]])
+
+
+# ----------------------------------------------------------------------------- LogBarrieriLQR
+BARRIER_TAGS = [("LogBarrier_TwoLink_T100", "TwoLinkPlanarManipulator"), ("LogBarrier_ThreeLink_T100", "ThreeLinkPlanarManipulator"),
+                ("LogBarrier_RoboticArm_T100", "RoboticArmTracking")]
+_BARRIER_PROBLEMS = {}
+
+
+def barrier_problems(model, T, t0=0.5):
+    """(Problem of the barrier cost, Problem of the plain cost), both on the reference's substrate."""
+    from conftest import make_scenario
+    key = (model, T)
+    if key not in _BARRIER_PROBLEMS:
+        numba = model == "RoboticArmTracking"
+        sc = make_scenario(model, T)
+        _BARRIER_PROBLEMS[key] = (orc.Problem(orc.BarrierScenario(sc, t0), use_numba=numba), make_problem(model, T))
+    return _BARRIER_PROBLEMS[key]
+
+
+@pytest.mark.parametrize("tag,model", BARRIER_TAGS)
+def test_log_barrier_cost_derivatives(golden, tag, model):
+    """Barrier cost, gradient and Hessian diagonal at the initial trajectory, t = t[0]: bit-equal to the reference."""
+    g = golden(tag)
+    pb, _ = barrier_problems(model, 100)
+    X = orc.rollout(pb)
+    assert np.array_equal(X, g["init_X"])
+    assert orc.cost(pb, X) == float(g["init_J"])
+    _F, c, C = orc.derivs(pb, X)
+    assert np.array_equal(c, g["init_c"])
+    assert np.array_equal(np.stack([np.diag(Ct) for Ct in C]), g["init_Cdiag"])
+
+
+@pytest.mark.parametrize("tag,model", BARRIER_TAGS)
+def test_log_barrier_default_solve(golden, tag, model):
+    """LogBarrieriLQR.solve on the scenario's default problem: iterations of every inner loop, step indices,
+    barrier and real cost per iteration and the final trajectory - all as the reference produced them."""
+    g = golden(tag)
+    pb, pr = barrier_problems(model, 100)
+    res = orc.solve_log_barrier(pb, pr, t_list=tuple(g["t_list"]), max_line_search=int(g["max_line_search"]))
+    assert list(res["inner_iters"]) == list(g["def_inner_iters"])
+    assert np.array_equal(res["alphas"], g["def_alpha"])
+    assert np.array_equal(res["Js"], g["def_J"])
+    assert np.array_equal(res["Jreals"], g["def_Jreal"])
+    assert np.array_equal(res["X"], g["def_X"])

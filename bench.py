@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--horizon", type=int, default=100)
     ap.add_argument("--dtype", default="float64", choices=["float64", "float32"])
     ap.add_argument("--model", default=MODEL)
+    ap.add_argument("--solver", default="basic", choices=["basic", "logbarrier"],
+                    help="basic = BasiciLQR (the headline); logbarrier = LogBarrieriLQR (SURVEY 8(f) N1): a step is one "
+                         "solve_batch = one inner iLQR loop per barrier parameter t in [0.5 .. 100]")
     ap.add_argument("--mode", default="converge", choices=["converge", "fixed"],
                     help="converge: reference defaults; fixed: is_check_stop=False, max_iter=20")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -128,7 +131,7 @@ class ClockSampler:
 _WORKER = {}
 
 
-def _cpu_init(model, T, barrier):
+def _cpu_init(model, T, barrier, solver="basic"):
     """Per-process set-up: build the oracle problem and pay the numba JIT once (untimed, as the
     reference itself excludes its compile iteration, basic_ilqr.py:82-83)."""
     for var in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "NUMBA_NUM_THREADS", "MKL_NUM_THREADS"):
@@ -138,10 +141,15 @@ def _cpu_init(model, T, barrier):
     import curiousrl_b200.scenario.dynamic_model as models
     from curiousrl_b200.utils.synthetic import synthetic_batch
     from oracle import ilqr_numpy as orc                 # CPU baseline / reference arm: the one place bench.py runs the oracle
-    prob = orc.Problem(getattr(models, model)(T=T), use_numba=True)
+    sc = getattr(models, model)(T=T)
+    prob = orc.Problem(sc, use_numba=True)
     x0, tgt = synthetic_batch(model, 1, seed=99)
     orc.solve(prob, x0[0], tgt[0], max_line_search=MAX_LINE_SEARCH, max_iter=3)
-    _WORKER["prob"], _WORKER["orc"], _WORKER["barrier"] = prob, orc, barrier
+    _WORKER["prob"], _WORKER["orc"], _WORKER["barrier"], _WORKER["prob_barrier"] = prob, orc, barrier, None
+    if solver == "logbarrier":
+        pb = orc.Problem(orc.BarrierScenario(sc, 0.5), use_numba=True)
+        orc.solve_log_barrier(pb, prob, x0[0], tgt[0], max_line_search=MAX_LINE_SEARCH, max_iter=2)
+        _WORKER["prob_barrier"] = pb
 
 
 def _cpu_solve(job):
@@ -149,20 +157,24 @@ def _cpu_solve(job):
     orc, prob = _WORKER["orc"], _WORKER["prob"]
     t0 = time.perf_counter()
     iters = 0
+    pb = _WORKER["prob_barrier"]
     for b in range(x0.shape[0]):
-        iters += orc.solve(prob, x0[b], tgt[b], max_line_search=MAX_LINE_SEARCH)["iters"]
+        if pb is None:
+            iters += orc.solve(prob, x0[b], tgt[b], max_line_search=MAX_LINE_SEARCH)["iters"]
+        else:
+            iters += int(orc.solve_log_barrier(pb, prob, x0[b], tgt[b], max_line_search=MAX_LINE_SEARCH)["inner_iters"].sum())
     return iters, time.perf_counter() - t0
 
 
 class CpuReference:
     """Pool of one worker per host core, each running the CPU oracle port single-threaded."""
 
-    def __init__(self, model, T, cores=None):
+    def __init__(self, model, T, cores=None, solver="basic"):
         import multiprocessing as mp
         self.model = model
         self.cores = cores or min(os.cpu_count() or 1, 64)
         ctx = mp.get_context("spawn")
-        self.pool = ctx.Pool(self.cores, initializer=_cpu_init, initargs=(model, T, ctx.Barrier(self.cores)))
+        self.pool = ctx.Pool(self.cores, initializer=_cpu_init, initargs=(model, T, ctx.Barrier(self.cores), solver))
         self.pool.map(_ready, range(self.cores), chunksize=1)   # returns once every worker finished its JIT warm-up
 
     def run(self, per_core, seed):
@@ -191,7 +203,7 @@ def run_reference(args):
     if rank != 0:
         return
     per_core = args.cpu_sample or 64
-    ref = CpuReference(args.model, args.horizon)
+    ref = CpuReference(args.model, args.horizon, solver=args.solver)
     iters_tot, wall_tot = 0, 0.0
     for step in range(args.warmup + args.steps):
         iters, wall = ref.run(per_core, seed=1234)
@@ -213,9 +225,11 @@ def run_reference(args):
 
 
 def workload_config(args, n_gpus):
-    return {"workload": "%s iLQR, batch %d random initial states per GPU, T=%d, %s, BasiciLQR(max_line_search=%d), %s" % (
-                args.model, args.batch, args.horizon, "FP64" if args.dtype == "float64" else "FP32", MAX_LINE_SEARCH,
+    return {"workload": "%s iLQR, batch %d random initial states per GPU, T=%d, %s, %s(max_line_search=%d), %s" % (
+                args.model, args.batch, args.horizon, "FP64" if args.dtype == "float64" else "FP32",
+                "BasiciLQR" if args.solver == "basic" else "LogBarrieriLQR", MAX_LINE_SEARCH,
                 "to convergence (relative 1e-6, max_iter 1000)" if args.mode == "converge" else "fixed work (20 iterations)"),
+            "solver": args.solver,
             "model": args.model, "batch_per_gpu": args.batch, "global_batch": args.batch * n_gpus, "horizon": args.horizon,
             "mode": args.mode, "parallelism": "dp%d (independent shards, terminal gather of J/iters/flags)" % n_gpus,
             "cache": "working set (solver workspace ~2.1 GB + 0.6 GB results) exceeds the 126 MB L2; "
@@ -227,7 +241,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from curiousrl_b200 import logger
-    from curiousrl_b200.algorithm.ilqr_solver import BasiciLQR
+    from curiousrl_b200.algorithm.ilqr_solver import BasiciLQR, LogBarrieriLQR
     from curiousrl_b200.distributed import gather_results
     import curiousrl_b200.scenario.dynamic_model as models
     from curiousrl_b200.utils.synthetic import synthetic_batch
@@ -247,7 +261,12 @@ def run_b200(args):
     kw = dict(max_line_search=MAX_LINE_SEARCH, dtype=args.dtype, grid_blocks=args.grid_blocks)
     if args.mode == "fixed":
         kw.update(is_check_stop=False, max_iter=20)
-    algo = BasiciLQR(**kw).init(getattr(models, args.model)(T=T))
+    if args.solver == "logbarrier":
+        if args.mode != "converge" or args.dtype != "float64":
+            raise SystemExit("bench.py: --solver logbarrier runs to convergence in FP64")
+        algo = LogBarrieriLQR(max_line_search=MAX_LINE_SEARCH, grid_blocks=args.grid_blocks).init(getattr(models, args.model)(T=T))
+    else:
+        algo = BasiciLQR(**kw).init(getattr(models, args.model)(T=T))
     dm = algo._dev
     x0_h, tgt_h = synthetic_batch(args.model, B, seed=1234 + rank)
     np_dt = np.float64 if args.dtype == "float64" else np.float32
@@ -265,7 +284,7 @@ def run_b200(args):
 
     def step_device():
         nonlocal out
-        out = algo.solve_batch(x0_d, tgt_d, out=out)
+        out = algo.solve_batch(x0_d, tgt_d, out=out) if args.solver == "basic" else algo.solve_batch(x0_d, tgt_d)
         if world > 1:
             return gather_results(out.obj_fun_value, out.iterations, out.converged, total_B)
         return out
@@ -280,11 +299,13 @@ def run_b200(args):
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
+    launches0 = dm.launches + (algo._real_dev.launches if args.solver == "logbarrier" else 0)
     for i in range(args.steps):
         flush.zero_()
         starts[i].record()
         res = step_device()
         ends[i].record()
+    launches_timed = dm.launches + (algo._real_dev.launches if args.solver == "logbarrier" else 0) - launches0
     barrier()
     t_wall1 = time.time()
     ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
@@ -310,7 +331,10 @@ def run_b200(args):
     X_h = torch.empty((B, T, dm.d), dtype=dm.dtype).pin_memory()
 
     def step_e2e():
-        r = algo.solve_batch(x0_pin.to(dev, non_blocking=True), tgt_pin.to(dev, non_blocking=True), out=out)
+        if args.solver == "basic":
+            r = algo.solve_batch(x0_pin.to(dev, non_blocking=True), tgt_pin.to(dev, non_blocking=True), out=out)
+        else:
+            r = algo.solve_batch(x0_pin.to(dev, non_blocking=True), tgt_pin.to(dev, non_blocking=True))
         if world > 1:
             gather_results(r.obj_fun_value, r.iterations, r.converged, total_B)
         J_h.copy_(r.obj_fun_value, non_blocking=True)
@@ -349,7 +373,8 @@ def run_b200(args):
             "config": workload_config(args, world),
             "traj_iters_per_step": iters_all, "converged_fraction": conv_all / total_B,
             "mean_iters_per_traj": iters_all / total_B,
-            "gpu_launches": args.steps,       # one persistent solve_kernel per step (+ one memset node of its control block)
+            "gpu_launches": launches_timed,   # BasiciLQR: one persistent solve_kernel per step (+ one memset node of its control
+                                              # block); LogBarrieriLQR: one per barrier parameter + the real-cost kernel
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3},
@@ -357,14 +382,14 @@ def run_b200(args):
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_traj_iter": bpi,
                          "algorithmic_bytes_per_launch": iters_local * bpi}}
-    tr = profiled_traffic(args.model, args.dtype, B, args.mode)
+    tr = profiled_traffic(args.model, args.dtype, B, args.mode) if args.solver == "basic" else None   # captured for BasiciLQR only
     if tr is not None:
         line["roofline"]["traffic"] = tr["dram_bytes"]
         line["roofline"]["traffic_source"] = tr.get("source")
     if world == 1 and not args.no_cpu_baseline:
         per_core = args.cpu_sample or 256           # the first 256 x cores trajectories (~15-20 s)
         try:
-            ref = CpuReference(args.model, T)
+            ref = CpuReference(args.model, T, solver=args.solver)
             iters, wall = ref.run(per_core, seed=1234)
             ref.close()
             line["cpu_baseline"] = {"value": iters / wall, "unit": UNIT, "cores": ref.cores, "kind": "port",

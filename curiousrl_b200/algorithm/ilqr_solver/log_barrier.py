@@ -10,8 +10,7 @@ the stored cost to +inf after each converged inner loop (:121-146).
 Device side: the same kernels as BasiciLQR, instantiated for the barrier cost (`Barrier<Model>` in
 csrc/ilqr_models.cuh, model ids CRL_*_BARRIER) - non-constant action entries of the cost gradient and
 Hessian inside the fused Riccati pass, `log` terms in every rollout's cost.  One inner loop = one
-`crl_solve` launch warm-started with the previous loop's actions.  FP64 only; the lane-per-trajectory
-kernel runs the whole solve (the cooperative tail engine is compiled for the plain costs only).
+`crl_solve` launch warm-started with the previous loop's actions.  FP64 only.
 
 Quirks kept:
 * the FIRST backward pass after t moves on still uses cost derivatives evaluated with the previous t
@@ -56,11 +55,11 @@ class LogBarrierBatchResult(BatchResult):
 
 class LogBarrieriLQR(iLQRWrapper):
     """Log-barrier iLQR (log_barrier_ilqr.py:13-156) on the GPU.  Constructor arguments as in the reference;
-    `device`, `verify`, `grid_blocks` as for BasiciLQR."""
+    `device`, `verify`, `grid_blocks`, `occupancy`, `coop_threshold` as for BasiciLQR."""
 
     def __init__(self, max_iter=1000, is_check_stop=True, stopping_criterion=1e-6, max_line_search=50, gamma=0.5,
                  t=[0.5, 1., 2., 5., 10., 20., 50., 100.], line_search_method="feasibility", stopping_method="relative",
-                 device=None, verify=True, grid_blocks=0):
+                 device=None, verify=True, grid_blocks=0, occupancy=0, coop_threshold=0):
         super().__init__(stopping_criterion=stopping_criterion, max_line_search=max_line_search, gamma=gamma,
                          line_search_method=line_search_method, stopping_method=stopping_method,
                          max_iter=max_iter, is_check_stop=is_check_stop)
@@ -70,7 +69,8 @@ class LogBarrieriLQR(iLQRWrapper):
         self._device = device
         self._verify = verify
         self._grid_blocks = grid_blocks
-        self._coop_threshold = -1            # barrier models run on the lane-per-trajectory kernel only
+        self._occupancy = occupancy          # scheduling knobs as for BasiciLQR; results do not depend on them
+        self._coop_threshold = coop_threshold
         self._trajectory = None
         self._t_stale = None                 # the t the next first backward pass still sees
         self.last_result: Optional[BatchResult] = None

@@ -28,6 +28,33 @@ template <class Mdl> struct CoopSupport { static constexpr bool value = false; }
 template <> struct CoopSupport<TwoLink> { static constexpr bool value = true; };
 template <> struct CoopSupport<ThreeLink> { static constexpr bool value = true; };
 template <> struct CoopSupport<RoboticArm> { static constexpr bool value = true; };
+// the log-barrier variants run on the column-group passes (the action entries of the cost gradient / Hessian
+// are the only difference: coop_cost_u below); the element-per-lane and pair-group passes are plain-cost only
+template <class Base> struct CoopSupport<Barrier<Base>> { static constexpr bool value = CoopSupport<Base>::value; };
+
+// kinematic chain (constant A, B; colgroup_backward) or rigid arm (dense variable rows; colgroup_backward_arm)
+template <class Mdl> struct IsChain { static constexpr bool value = true; };
+template <> struct IsChain<RoboticArm> { static constexpr bool value = false; };
+template <> struct IsChain<Barrier<RoboticArm>> { static constexpr bool value = false; };
+
+// Action entries of the cost gradient and Hessian at one time step: constants for the plain costs; for the
+// barrier costs they depend on u and on the barrier parameter in the parameter row (tb = p[kT], or the stale
+// p[kT + 1] in the first backward pass of a solve).
+template <class Mdl, class R>
+__device__ __forceinline__ void coop_cost_u(const R (&u)[Mdl::M], R tb, R (&grad)[Mdl::M], R (&hess)[Mdl::M]) {
+    R pp[Mdl::P];
+    CRL_UNROLL for (int i = 0; i < Mdl::P; ++i) pp[i] = R(0);
+    if constexpr (Mdl::kBarrier) pp[Mdl::kT] = tb;
+    CRL_UNROLL for (int a = 0; a < Mdl::M; ++a) {
+        grad[a] = cost_grad<Mdl, R>(Mdl::N + a, u[a], pp);
+        hess[a] = cost_hess_u<Mdl, R>(a, u[a], pp);
+    }
+}
+template <class Mdl, class R>
+__device__ __forceinline__ R coop_barrier_t(const ParamRef<R>& prm, int t, bool first) {
+    if constexpr (Mdl::kBarrier) return prm.get(t, first ? Mdl::kT + 1 : Mdl::kT);
+    else return R(0);
+}
 
 // Shared-memory layout (in reals) of the cooperative backward pass of ONE trajectory.
 template <class Mdl>
@@ -88,6 +115,7 @@ struct CoopTraj {
     R* k;
     R* G;
     bool on;
+    bool first;                     // barrier costs: this is the first backward pass of the solve (stale t, see Barrier)
 };
 
 // Tables of the variable Jacobian entries of NQ trajectories, all time steps: lanes take time steps
@@ -415,7 +443,7 @@ __device__ void colgroup_backward(const CoopTraj<R> (&tr)[4], int T, R* S, int l
     vy[0] = vy[1] = vyy[0] = vyy[1] = R(0);
 
     // row values, one step ahead: G row (2J), x_i of the odd rows (J), u (M), output entries (2), targets (2)
-    R Gn[2 * J], xo_n[J], u_n[M], y_n[2], p_n[2];
+    R Gn[2 * J], xo_n[J], u_n[M], y_n[2], p_n[2], tbar_n;
     {
         const size_t r = (size_t)(T - 1);
         const size_t rs = (size_t)me.rs;
@@ -423,6 +451,7 @@ __device__ void colgroup_backward(const CoopTraj<R> (&tr)[4], int T, R* S, int l
         CRL_UNROLL for (int j = 0; j < J; ++j) xo_n[j] = me.X[r * rs + 2 * j + 1];
         CRL_UNROLL for (int a = 0; a < M; ++a) u_n[a] = me.X[r * rs + N + a];
         CRL_UNROLL for (int y = 0; y < 2; ++y) { y_n[y] = me.X[r * rs + NS + y]; p_n[y] = me.prm.get(T - 1, y); }
+        tbar_n = coop_barrier_t<Mdl, R>(me.prm, T - 1, me.first);
     }
 
     for (int t = T - 1; t >= 0; --t) {
@@ -431,6 +460,8 @@ __device__ void colgroup_backward(const CoopTraj<R> (&tr)[4], int T, R* S, int l
         CRL_UNROLL for (int j = 0; j < J; ++j) xo[j] = xo_n[j];
         CRL_UNROLL for (int a = 0; a < M; ++a) u[a] = u_n[a];
         CRL_UNROLL for (int y = 0; y < 2; ++y) { yv[y] = y_n[y]; pv[y] = p_n[y]; }
+        R gu[M], hu[M];                                       // barrier costs: action entries of the cost gradient / Hessian
+        if constexpr (Mdl::kBarrier) coop_cost_u<Mdl, R>(u, tbar_n, gu, hu);
         {
             const size_t r = (size_t)(t > 0 ? t - 1 : 0);
             const size_t rs = (size_t)me.rs;
@@ -438,6 +469,7 @@ __device__ void colgroup_backward(const CoopTraj<R> (&tr)[4], int T, R* S, int l
             CRL_UNROLL for (int j = 0; j < J; ++j) xo_n[j] = me.X[r * rs + 2 * j + 1];
             CRL_UNROLL for (int a = 0; a < M; ++a) u_n[a] = me.X[r * rs + N + a];
             CRL_UNROLL for (int y = 0; y < 2; ++y) { y_n[y] = me.X[r * rs + NS + y]; p_n[y] = me.prm.get((int)r, y); }
+            tbar_n = coop_barrier_t<Mdl, R>(me.prm, (int)r, me.first);
         }
         // ---- column c of A^T V and B^T V (affine lane: A^T v, B^T v)
         R MA[NS], MB[M];
@@ -448,7 +480,8 @@ __device__ void colgroup_backward(const CoopTraj<R> (&tr)[4], int T, R* S, int l
         CRL_UNROLL for (int a = 0; a < M; ++a)
             CRL_UNROLL for (int b = 0; b < M; ++b) {
                 const R acc = __shfl_sync(0xffffffffu, MB[a], 2 * b + 1, GS) * h;
-                Quu[a][b] = (a == b) ? R(cost_hess<Mdl>(N + a)) + acc : acc;
+                if constexpr (Mdl::kBarrier) Quu[a][b] = (a == b) ? hu[a] + acc : acc;
+                else Quu[a][b] = (a == b) ? R(cost_hess<Mdl>(N + a)) + acc : acc;
             }
         LuFactors<M, R> lu;
         lu_factor<M, R>(Quu, lu);
@@ -480,7 +513,9 @@ __device__ void colgroup_backward(const CoopTraj<R> (&tr)[4], int T, R* S, int l
         CRL_UNROLL for (int a = 0; a < M; ++a) {
             const R left = __shfl_up_sync(0xffffffffu, MB[a], 1, GS);
             const R col = c_odd ? left * h + MB[a] : MB[a];
-            const R aff = R(2.0 * Mdl::weight(N)) * u[a] + MB[a];
+            R aff;
+            if constexpr (Mdl::kBarrier) aff = gu[a] + MB[a];
+            else aff = R(2.0 * Mdl::weight(N)) * u[a] + MB[a];
             Qu[a][0] = is_aff ? aff : col;
         }
         // ---- gains of this column
@@ -557,6 +592,7 @@ struct PairGroup {
 template <class Mdl, class R>
 __device__ void pairgroup_backward(const CoopTraj<R> (&tr)[8], int T, R* S, int lane) {
     using PG = PairGroup<Mdl>;
+    static_assert(!Mdl::kBarrier, "the pair-group pass is written for the plain costs");
     constexpr int NS = Mdl::NS, M = Mdl::M, J = Mdl::M, N = Mdl::N, GS = PG::GS, NG = PG::NG;
     const R h = R(kH);
     const int g = lane / GS, p = lane % GS;
@@ -731,9 +767,8 @@ __device__ void pairgroup_backward(const CoopTraj<R> (&tr)[8], int T, R* S, int 
 // all time steps in parallel (lanes over t; Mdl::coop_table).  Per element the operation sequence is
 // riccati_step's with the structural zeros / ones / h of RoboticArm::akind pruned the same way:
 // a product with the literal 1 (x * 1, fma(x, 1, acc)) stands for the plain copy / addition there.
-template <class R>
+template <class Mdl, class R>
 __device__ void colgroup_backward_arm(const CoopTraj<R> (&tr)[4], int T, R* S, int lane) {
-    using Mdl = RoboticArm;
     using CG = ColGroup<Mdl>;
     constexpr int NS = Mdl::NS, M = Mdl::M, N = Mdl::N, D = Mdl::D, GS = CG::GS, NG = CG::NG, TAB = Mdl::kCoopTab;
     static_assert(NS == 4 && M == 2 && TAB == 16, "written for the 4-state / 2-action arm");
@@ -766,13 +801,14 @@ __device__ void colgroup_backward_arm(const CoopTraj<R> (&tr)[4], int T, R* S, i
     vy[0] = vy[1] = vyy[0] = vyy[1] = R(0);
 
     // row values, one step ahead: the table (16), x_1, x_3 (cost gradient), u (2), output entries (2), targets (2)
-    R tb_n[TAB], xo_n[2], u_n[M], y_n[2], p_n[2];
+    R tb_n[TAB], xo_n[2], u_n[M], y_n[2], p_n[2], tbar_n;
     {
         const size_t r = (size_t)(T - 1), rs = (size_t)me.rs;
         CRL_UNROLL for (int i = 0; i < TAB; ++i) tb_n[i] = me.G[r * TAB + i];
         CRL_UNROLL for (int j = 0; j < 2; ++j) xo_n[j] = me.X[r * rs + 2 * j + 1];
         CRL_UNROLL for (int a = 0; a < M; ++a) u_n[a] = me.X[r * rs + N + a];
         CRL_UNROLL for (int y = 0; y < 2; ++y) { y_n[y] = me.X[r * rs + NS + y]; p_n[y] = me.prm.get(T - 1, y); }
+        tbar_n = coop_barrier_t<Mdl, R>(me.prm, T - 1, me.first);
     }
 
     for (int t = T - 1; t >= 0; --t) {
@@ -783,12 +819,15 @@ __device__ void colgroup_backward_arm(const CoopTraj<R> (&tr)[4], int T, R* S, i
         CRL_UNROLL for (int j = 0; j < 2; ++j) xo[j] = xo_n[j];
         CRL_UNROLL for (int a = 0; a < M; ++a) u[a] = u_n[a];
         CRL_UNROLL for (int y = 0; y < 2; ++y) { yv[y] = y_n[y]; pv[y] = p_n[y]; }
+        R gu[M], hu[M];                                       // barrier costs: action entries of the cost gradient / Hessian
+        if constexpr (Mdl::kBarrier) coop_cost_u<Mdl, R>(u, tbar_n, gu, hu);
         {
             const size_t r = (size_t)(t > 0 ? t - 1 : 0), rs = (size_t)me.rs;
             CRL_UNROLL for (int i = 0; i < TAB; ++i) tb_n[i] = me.G[r * TAB + i];
             CRL_UNROLL for (int j = 0; j < 2; ++j) xo_n[j] = me.X[r * rs + 2 * j + 1];
             CRL_UNROLL for (int a = 0; a < M; ++a) u_n[a] = me.X[r * rs + N + a];
             CRL_UNROLL for (int y = 0; y < 2; ++y) { y_n[y] = me.X[r * rs + NS + y]; p_n[y] = me.prm.get((int)r, y); }
+            tbar_n = coop_barrier_t<Mdl, R>(me.prm, (int)r, me.first);
         }
         // ---- column c of A^T V and B^T V (affine lane: A^T v, B^T v); l ascending over the non-zero A[l][i]
         R MA[NS], MB[M];
@@ -803,7 +842,8 @@ __device__ void colgroup_backward_arm(const CoopTraj<R> (&tr)[4], int T, R* S, i
             const R m1 = __shfl_sync(0xffffffffu, MB[a], 1, GS), m3 = __shfl_sync(0xffffffffu, MB[a], 3, GS);
             CRL_UNROLL for (int b = 0; b < M; ++b) {
                 const R acc = fmadd(m3, B3[b], m1 * B1[b]);
-                Quu[a][b] = (a == b) ? R(cost_hess<Mdl>(N + a)) + acc : acc;
+                if constexpr (Mdl::kBarrier) Quu[a][b] = (a == b) ? hu[a] + acc : acc;
+                else Quu[a][b] = (a == b) ? R(cost_hess<Mdl>(N + a)) + acc : acc;
             }
         }
         LuFactors<M, R> lu;
@@ -842,7 +882,9 @@ __device__ void colgroup_backward_arm(const CoopTraj<R> (&tr)[4], int T, R* S, i
             R col = (lo ? r0 : r1) * c_first;
             col = fmadd(lo ? r1 : r2, c_second, col);
             col = fmadd(r3, a3c, col);
-            const R aff = R(2.0 * Mdl::weight(N)) * u[a] + MB[a];
+            R aff;
+            if constexpr (Mdl::kBarrier) aff = gu[a] + MB[a];
+            else aff = R(2.0 * Mdl::weight(N)) * u[a] + MB[a];
             Qu[a][0] = is_aff ? aff : col;
         }
         // ---- gains of this column

@@ -431,6 +431,7 @@ __device__ __noinline__ double coop_rollout(const R* X, const R* K, const R* k, 
 // the element-per-lane pass exists for the kinematic chains only
 template <class Mdl> struct HasElementPass { static constexpr bool value = true; };
 template <> struct HasElementPass<RoboticArm> { static constexpr bool value = false; };
+template <class Base> struct HasElementPass<Barrier<Base>> { static constexpr bool value = false; };   // plain costs only
 
 template <class Mdl, class R, int NT>
 __device__ __noinline__ void coop_backward_call(const CoopTraj<R> (&tr)[NT], int T, R* S, int lane) {
@@ -438,8 +439,8 @@ __device__ __noinline__ void coop_backward_call(const CoopTraj<R> (&tr)[NT], int
         static_assert(HasElementPass<Mdl>::value, "the pair-group pass (NT = 8) is written for the kinematic chains");
         pairgroup_backward<Mdl, R>(tr, T, S, lane);
     } else if constexpr (NT == ColGroup<Mdl>::NG) {
-        if constexpr (HasElementPass<Mdl>::value) colgroup_backward<Mdl, R>(tr, T, S, lane);
-        else colgroup_backward_arm<R>(tr, T, S, lane);
+        if constexpr (IsChain<Mdl>::value) colgroup_backward<Mdl, R>(tr, T, S, lane);
+        else colgroup_backward_arm<Mdl, R>(tr, T, S, lane);
     } else {
         static_assert(HasElementPass<Mdl>::value, "this model only has the column-group pass (NT = 4)");
         coop_backward<Mdl, R, NT>(tr, T, S, lane);
@@ -680,6 +681,7 @@ __device__ void coop_engine(const SolveArgs<R>& a, Source& src, R* xscr, R* gscr
             tr[q].k = g + TK;
             tr[q].G = g + TK + Tk;
             tr[q].on = on;
+            tr[q].first = s_it[q] == 0;
         }
         {
             // a warp that holds a single trajectory (the end of the tail) steps it alone: lowest latency
@@ -1391,8 +1393,8 @@ struct CoopVariant {
         case 12: { using V = SolveVariant<Mdl, R, 4, 2, true>; __VA_ARGS__; } break;  \
         case 20: { CRL_COOP_VARIANT(4, 2, kCoopNTFor<Mdl>, __VA_ARGS__) } break;         \
         case 21: { CRL_COOP_VARIANT(4, 3, kCoopNTFor<Mdl>, __VA_ARGS__) } break;         \
-        case 22: { CRL_COOP_VARIANT(4, 2, 2, __VA_ARGS__) } break;                       \
-        case 23: { CRL_COOP_VARIANT(4, 2, 8, __VA_ARGS__) } break;                       \
+        case 22: if constexpr (!Mdl::kBarrier) { CRL_COOP_VARIANT(4, 2, 2, __VA_ARGS__) } break;   \
+        case 23: if constexpr (!Mdl::kBarrier) { CRL_COOP_VARIANT(4, 2, 8, __VA_ARGS__) } break;   \
         default: break;                                                            \
     }
 #else

@@ -110,3 +110,17 @@ def test_unsupported_inputs_raise():
     import curiousrl_b200.scenario.dynamic_model as models
     with pytest.raises(Exception):
         LogBarrieriLQR().init(models.RoboticArmTracking(is_with_constraints=False))     # no action box: no barrier model
+
+
+@pytest.mark.parametrize("model,B", [("ThreeLinkPlanarManipulator", 192), ("RoboticArmTracking", 160), ("TwoLinkPlanarManipulator", 96)])
+def test_every_scheduling_path_gives_the_same_bits(model, B):
+    """Barrier costs through the lane-per-trajectory kernel only, the lane kernel with the cooperative tail, and the
+    cooperative engine as the whole solve (the default at this batch size): bit-identical results."""
+    from curiousrl_b200.utils.synthetic import synthetic_batch
+    x0, tgt = synthetic_batch(model, B, seed=7)
+    ref = make_algo(model, verify=False, occupancy=12, coop_threshold=-1, max_iter=150).solve_batch(x0, tgt)
+    assert int(ref.inner_iterations[:, 0].max()) > 40
+    for kw in (dict(), dict(occupancy=12), dict(occupancy=12, coop_threshold=32), dict(occupancy=20), dict(occupancy=21)):
+        res = make_algo(model, verify=False, max_iter=150, **kw).solve_batch(x0, tgt)
+        for f in ("inner_iterations", "iterations", "converged", "obj_fun_value", "trajectory", "real_obj_fun_value"):
+            assert torch.equal(getattr(res, f), getattr(ref, f)), "%s differs with %s" % (f, kw)

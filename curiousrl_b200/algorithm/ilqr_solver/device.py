@@ -229,3 +229,33 @@ class DeviceModel:
         # keep inputs alive until the stream has consumed them
         out._keepalive = (x0, params, u0t, J_init)
         return out
+
+    def solve_stages(self, opts: _native.SolverOpts, x0, stage_params, u0=None, J_init=None, return_trajectory=True):
+        """crl_solve_stages: every trajectory runs one inner loop per stage row inside ONE persistent kernel.
+        stage_params [B, S, p] (or [1, S, p] shared).  Returns (BatchResult, stage_iterations [B, S] int32)."""
+        x0 = self.real(x0).reshape(-1, self.n)
+        B = x0.shape[0]
+        stage_params = self.real(stage_params)
+        if stage_params.dim() != 3 or stage_params.shape[-1] != self.p or stage_params.shape[0] not in (1, B):
+            raise ValueError("stage_params must be [B, S, p] or [1, S, p]")
+        S = int(stage_params.shape[1])
+        sb = 0 if (stage_params.shape[0] == 1 and B != 1) else S * self.p
+        prob = _native.Problem(self.model_id, self.dtype_id, B, self.T, 0, sb, stage_params.data_ptr(), self.u_lo, self.u_hi)
+        u0t, u0s = self._u0(u0, B)
+        ws = self.workspace(prob, opts)
+        if J_init is not None:
+            J_init = torch.as_tensor(J_init, dtype=torch.float64).to(self.device).reshape(-1)
+            if J_init.numel() == 1:
+                J_init = J_init.expand(B)
+            J_init = J_init.contiguous()
+        out = BatchResult(self.empty(B, self.T, self.d) if return_trajectory else None,
+                          self.empty(B, dtype=torch.float64), self.empty(B, dtype=torch.int32),
+                          self.empty(B, dtype=torch.uint8))
+        stage_iters = torch.zeros((B, S), dtype=torch.int32, device=self.device)
+        _native.check(self.lib.crl_solve_stages(prob, ctypes.byref(opts), S, _ptr(x0), _ptr(u0t), u0s, _ptr(J_init),
+                                                _ptr(out.trajectory), _ptr(out.obj_fun_value), _ptr(out.iterations),
+                                                _ptr(out.converged), _ptr(stage_iters), _ptr(ws), ws.numel(),
+                                                self._stream()), "crl_solve_stages")
+        self.launches += 1       # one persistent kernel for the whole barrier schedule
+        out._keepalive = (x0, stage_params, u0t, J_init)
+        return out, stage_iters

@@ -31,7 +31,7 @@ import torch
 from ... import _native
 from ...utils.Logger import logger
 from .device import BatchResult, DeviceModel
-from .solver import iLQRDynamicModel, iLQRObjectiveFunction, iLQRWrapper, _np
+from .solver import iLQRDynamicModel, iLQRObjectiveFunction, iLQRWrapper, _np, _publish_batch
 
 
 class _RealCostOwner:
@@ -174,10 +174,15 @@ class LogBarrieriLQR(iLQRWrapper):
         logger.info("[+ +] Completed! All Time:%.5e" % (_time.time() - start))
 
     # ------------------------------------------------------------------ batched extension
-    def solve_batch(self, init_state, add_param=None, init_action=None, return_trajectory=True) -> LogBarrierBatchResult:
-        """B independent problems: one `crl_solve` launch per barrier parameter, every launch warm-started with the
-        previous one's actions.  init_state [B, n]; add_param [B, p] constant targets (None = the scenario's);
-        init_action None (the scenario's), [T, m] or [B, T, m].  Fresh problems: the stored cost starts at +inf."""
+    def solve_batch(self, init_state, add_param=None, init_action=None, return_trajectory=True,
+                    fused=True) -> LogBarrierBatchResult:
+        """B independent problems.  init_state [B, n]; add_param [B, p] constant targets (None = the scenario's);
+        init_action None (the scenario's), [T, m] or [B, T, m].  Fresh problems: the stored cost starts at +inf.
+
+        fused=True (default): the whole barrier schedule in ONE persistent kernel (`crl_solve_stages`) - every
+        trajectory walks through the t's at its own pace, so the batch has one tail instead of one per t.
+        fused=False: one `crl_solve` launch per t, every launch warm-started with the previous one's actions
+        (the first implementation; same results bit for bit, kept for the equality test)."""
         dev, rdev = self._dev, self._real_dev
         x0 = dev.real(init_state).reshape(-1, dev.n)
         B = x0.shape[0]
@@ -185,30 +190,42 @@ class LogBarrieriLQR(iLQRWrapper):
             tgt = dev.real(np.asarray(self._obj_fun._add_param, dtype=np.float64)[0, :rdev.p]).reshape(1, rdev.p).expand(B, rdev.p)
         else:
             tgt = dev.real(add_param).reshape(B, rdev.p)
-        prm = torch.empty((B, dev.p), device=dev.device, dtype=dev.dtype)
-        prm[:, :rdev.p] = tgt
         u0 = self._dynamic_model._init_action if init_action is None else init_action
         if isinstance(u0, np.ndarray) and not u0.any():
             u0 = None
-        J_init = torch.full((B,), float("inf"), dtype=torch.float64, device=dev.device)
-        inner = torch.zeros((B, len(self._t)), dtype=torch.int32, device=dev.device)
         opts = self._opts(self._max_iter, self._is_check_stop)
-        res = None
-        t_prev = self._t[0]
-        for s, t in enumerate(self._t):
-            prm[:, rdev.p] = t
-            prm[:, rdev.p + 1] = t_prev
-            res = dev.solve(opts, x0, prm, u0=u0, J_init=J_init, return_trajectory=True)
-            inner[:, s] = res.iterations
-            u0 = res.trajectory[:, :, dev.n:].contiguous()
-            if self._is_check_stop:
-                J_init = torch.where(res.converged.bool(), torch.full_like(res.obj_fun_value, float("inf")), res.obj_fun_value)
-            else:
-                J_init = res.obj_fun_value.clone()
-            t_prev = t
+        S = len(self._t)
+        if fused:
+            # parameter rows [B, S, p]: (targets, t_s, t_{s-1}); the first loop's stale value is its own t
+            ts = torch.tensor(self._t, dtype=dev.dtype, device=dev.device)
+            prm = torch.empty((B, S, dev.p), device=dev.device, dtype=dev.dtype)
+            prm[:, :, :rdev.p] = tgt.reshape(B, 1, rdev.p)
+            prm[:, :, rdev.p] = ts
+            prm[:, 0, rdev.p + 1] = ts[0]
+            prm[:, 1:, rdev.p + 1] = ts[:-1]
+            res, inner = dev.solve_stages(opts, x0, prm, u0=u0, J_init=None, return_trajectory=True)
+        else:
+            prm = torch.empty((B, dev.p), device=dev.device, dtype=dev.dtype)
+            prm[:, :rdev.p] = tgt
+            J_init = torch.full((B,), float("inf"), dtype=torch.float64, device=dev.device)
+            inner = torch.zeros((B, S), dtype=torch.int32, device=dev.device)
+            res = None
+            t_prev = self._t[0]
+            for s, t in enumerate(self._t):
+                prm[:, rdev.p] = t
+                prm[:, rdev.p + 1] = t_prev
+                res = dev.solve(opts, x0, prm, u0=u0, J_init=J_init, return_trajectory=True)
+                inner[:, s] = res.iterations
+                u0 = res.trajectory[:, :, dev.n:].contiguous()
+                if self._is_check_stop:
+                    J_init = torch.where(res.converged.bool(), torch.full_like(res.obj_fun_value, float("inf")), res.obj_fun_value)
+                else:
+                    J_init = res.obj_fun_value.clone()
+                t_prev = t
         out = LogBarrierBatchResult(res.trajectory if return_trajectory else None, res.obj_fun_value, inner.sum(dim=1).to(torch.int32),
                                     res.converged)
         out.inner_iterations = inner
         out.real_obj_fun_value = rdev.cost(res.trajectory, tgt.contiguous())
         self.last_result = out
+        _publish_batch(self, out, inner_iterations=inner, real_obj_fun_value=out.real_obj_fun_value)
         return out

@@ -181,6 +181,45 @@ class iLQRWrapper(AlgoWrapper):
     def get_obj_add_param(self):
         return self._obj_fun._add_param
 
+    # -- batched re-solve (receding horizon) ---------------------------------------------------
+    def resolve_batch(self, previous, at_step, add_param=None, warm_start=False, **solve_kwargs):
+        """Batched form of the Examples' re-solve (Example/ThreeLinkPlanarManipulatorInteractive.py:18-31: new target,
+        `set_obj_fun_value(inf)`, `set_init_state(<state the arm is in>)`, `solve()`): every problem restarts from the
+        state its `previous` solution (a BatchResult with trajectories) reaches at `at_step` (an int, or one int per
+        problem), with `add_param` as its new target (None = as `solve_batch`) and the stored cost at +inf.
+
+        warm_start=False restarts from the scenario's `init_action` like the reference; warm_start=True starts from
+        the remaining actions of the previous solution shifted by `at_step` and padded with zeros (receding
+        horizon).  Everything stays on the device."""
+        dev = self._dev
+        X = previous.trajectory
+        if X is None:
+            raise ValueError("resolve_batch needs the trajectories of the previous solve (return_trajectory=True)")
+        B = X.shape[0]
+        steps = torch.as_tensor(at_step, device=X.device, dtype=torch.long).reshape(-1)
+        if steps.numel() == 1:
+            steps = steps.expand(B)
+        if steps.numel() != B or int(steps.min()) < 0 or int(steps.max()) >= dev.T:
+            raise ValueError("at_step must be an int or [B] ints in [0, T)")
+        x0 = X[torch.arange(B, device=X.device), steps, :dev.n].contiguous()
+        u0 = None
+        if warm_start:
+            t_idx = torch.arange(dev.T, device=X.device).reshape(1, dev.T) + steps.reshape(B, 1)        # [B, T]
+            valid = (t_idx < dev.T).unsqueeze(-1)
+            U = X[:, :, dev.n:]
+            u0 = torch.where(valid, torch.gather(U, 1, t_idx.clamp(max=dev.T - 1).unsqueeze(-1).expand(B, dev.T, dev.m)),
+                             torch.zeros((), dtype=U.dtype, device=U.device)).contiguous()
+        return self.solve_batch(x0, add_param, init_action=u0, **solve_kwargs)
+
+
+def _publish_batch(algo, res, **extra):
+    """Push a batched result to the logger's batched channel (the counterpart of `logger.save_to_json(trajectory=...)`
+    at the end of `solve()`); by reference unless `logger.set_is_save_json(True)`."""
+    fields = dict(trajectory=res.trajectory, obj_fun_value=res.obj_fun_value, iterations=res.iterations,
+                  converged=res.converged)
+    fields.update(extra)
+    logger.save_batch(meta={"solver": type(algo).__name__, "model": algo._dev.model_name, "T": algo._dev.T}, **fields)
+
 
 class BasiciLQR(iLQRWrapper):
     """Classical iLQR (basic_ilqr.py:12-104) on the GPU.
@@ -302,4 +341,5 @@ class BasiciLQR(iLQRWrapper):
                         J_init=obj_fun_value,
                         return_trajectory=return_trajectory, trace=trace, out=out)
         self.last_result = res
+        _publish_batch(self, res)
         return res

@@ -348,7 +348,29 @@ struct SolveArgs {
     unsigned long long* ctl;       // control block (zeroed per launch): see kCtl*
     QueueEntry* queue;             // straggler queue, one entry per lane of the grid
     int coop_threshold;            // a drained warp with <= this many live trajectories hands them over; < 0 = never
+    // Stage schedule (crl_solve_stages; barrier models): trajectory b runs one inner loop per parameter row
+    // params[b][0 .. n_stage) and keeps its trajectory in place between them.  n_stage <= 1 = a plain solve.
+    int n_stage;
+    int* stage_iters;              // [B][n_stage] iterations of every inner loop
 };
+
+// Stage schedules pack (stage, iteration) into the queue entry's / the engine's iteration word.
+constexpr int kStageShift = 24;
+constexpr int kStageItMask = (1 << kStageShift) - 1;
+
+// An inner loop of trajectory `traj` ended after `it` iterations in stage `stage`.  Returns true if the
+// trajectory goes on with the next stage (log_barrier_ilqr.py:121-146: same trajectory, next parameter row,
+// iteration counter back to 0, stored cost reset to +inf after a converged loop); otherwise writes the total
+// iteration count to *total.
+template <class R>
+__device__ __forceinline__ bool stage_advance(const SolveArgs<R>& a, long long traj, int stage, int it, int* total) {
+    __stcg(a.stage_iters + traj * a.n_stage + stage, it);
+    if (stage + 1 < a.n_stage) return true;
+    int sum = 0;
+    for (int s = 0; s < a.n_stage; ++s) sum += __ldcg(a.stage_iters + traj * a.n_stage + s);
+    *total = sum;
+    return false;
+}
 
 // Control block words.
 constexpr int kCtlNext = 0;        // next unassigned trajectory of the batch
@@ -644,9 +666,9 @@ __device__ void coop_engine(const SolveArgs<R>& a, Source& src, R* xscr, R* gscr
     const bool feas = a.op.ls_method == CRL_LS_FEASIBILITY;
     // slot state, identical in every lane: the current trajectory of slot q is candidate s_col[q] of its buffer s_buf[q]
     long long s_traj[NT];
-    int s_it[NT], s_buf[NT], s_col[NT];
+    int s_it[NT], s_buf[NT], s_col[NT], s_stage[NT];
     double s_J[NT];
-    CRL_UNROLL for (int q = 0; q < NT; ++q) { s_traj[q] = -1; s_it[q] = 0; s_buf[q] = 0; s_col[q] = 0; s_J[q] = 0.0; }
+    CRL_UNROLL for (int q = 0; q < NT; ++q) { s_traj[q] = -1; s_it[q] = 0; s_buf[q] = 0; s_col[q] = 0; s_J[q] = 0.0; s_stage[q] = 0; }
     // line-search role of this lane: candidate c_ls of trajectory q_ls
     const bool ls_lane = lane < NT * GL;
     const int q_ls = ls_lane ? lane / GL : 0, c_ls = ls_lane ? lane % GL : 0;
@@ -660,7 +682,15 @@ __device__ void coop_engine(const SolveArgs<R>& a, Source& src, R* xscr, R* gscr
             CRL_UNROLL for (int q = 0; q < NT; ++q) dst[q] = xscr + (size_t)(2 * q) * BUF;
             const unsigned got = src.template take<NT>(empty, dst, s_traj, s_it, s_J, lane);
             CRL_UNROLL for (int q = 0; q < NT; ++q)
-                if ((got >> q) & 1u) { s_buf[q] = 0; s_col[q] = 0; }
+                if ((got >> q) & 1u) {
+                    s_buf[q] = 0;
+                    s_col[q] = 0;
+                    s_stage[q] = 0;
+                    if constexpr (Mdl::kBarrier) {           // stage schedules: the source's iteration word carries the stage
+                        s_stage[q] = s_it[q] >> kStageShift;
+                        s_it[q] &= kStageItMask;
+                    }
+                }
             empty &= ~got;
         }
         tm.lap(PH_COOP_WAIT);
@@ -677,6 +707,7 @@ __device__ void coop_engine(const SolveArgs<R>& a, Source& src, R* xscr, R* gscr
             tr[q].X = xscr + (size_t)(2 * q + s_buf[q]) * BUF + s_col[q] * DP;
             tr[q].rs = RS;
             tr[q].prm = a.pb.prm(on ? s_traj[q] : 0);
+            if constexpr (Mdl::kBarrier) tr[q].prm.ptr += s_stage[q] * Mdl::P;
             tr[q].K = g;
             tr[q].k = g + TK;
             tr[q].G = g + TK + Tk;
@@ -786,9 +817,22 @@ __device__ void coop_engine(const SolveArgs<R>& a, Source& src, R* xscr, R* gscr
             }
             ++s_it[q];
             if ((stop && a.op.check_stop) || s_it[q] >= a.op.max_iter) {
+                int total = s_it[q];
+                if constexpr (Mdl::kBarrier) {
+                    if (a.n_stage > 1) {
+                        int go_on = 0;
+                        if (lane == 0) go_on = stage_advance<R>(a, s_traj[q], s_stage[q], s_it[q], &total) ? 1 : 0;
+                        if (__shfl_sync(kFull, go_on, 0) != 0) {
+                            ++s_stage[q];
+                            s_it[q] = 0;
+                            if (stop && a.op.check_stop) s_J[q] = (double)INFINITY;
+                            continue;
+                        }
+                    }
+                }
                 if (lane == 0) {
                     a.J_out[s_traj[q]] = s_J[q];
-                    a.iters_out[s_traj[q]] = s_it[q];
+                    a.iters_out[s_traj[q]] = total;
                     a.conv_out[s_traj[q]] = (stop && a.op.check_stop) ? 1 : 0;
                 }
                 if (a.X_out) {
@@ -1134,9 +1178,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) solve_kernel(SolveArgs<R> a)
             if (a.alpha_trace) a.alpha_trace[traj * a.op.max_iter + it] = (int8_t)taken;
             ++it;
             finished = (stop && a.op.check_stop) || it >= a.op.max_iter;
+            int total = it;
+            if constexpr (Mdl::kBarrier) {
+                if (finished && a.n_stage > 1) {
+                    const int stage = (int)((prm.ptr - a.pb.prm(traj).ptr) / Mdl::P);
+                    if (stage_advance<R>(a, traj, stage, it, &total)) {
+                        prm.ptr += Mdl::P;
+                        it = 0;
+                        if (stop && a.op.check_stop) J_last = (double)INFINITY;
+                        finished = false;
+                    }
+                }
+            }
             if (finished) {
                 a.J_out[traj] = J_last;
-                a.iters_out[traj] = it;
+                a.iters_out[traj] = total;
                 a.conv_out[traj] = (stop && a.op.check_stop) ? 1 : 0;
             }
         }
@@ -1181,7 +1237,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) solve_kernel(SolveArgs<R> a)
         const View<R, D, 32> Xc = cur ? Xbuf1 : Xbuf0;
         R* const xfree = a.ws + slot * a.slot_elems + lane_tiles_reals<Mdl>(T);   // engine scratch behind the tiles
         R* const gfree = xfree + coop_xscr_reals<Mdl, kCoopNTFor<Mdl>>(T);
-        publish_stragglers<R>(a, traj >= 0, traj, it, J_last, Xc.base, lane);
+        int it_word = it;
+        if constexpr (Mdl::kBarrier) {
+            if (traj >= 0 && a.n_stage > 1) it_word |= (int)((prm.ptr - a.pb.prm(traj).ptr) / Mdl::P) << kStageShift;
+        }
+        publish_stragglers<R>(a, traj >= 0, traj, it_word, J_last, Xc.base, lane);
         tm.lap(PH_RETIRE);
         StragglerSource<Mdl, R> src(a, gridDim.x * WARPS);
         coop_engine<Mdl, R, kCoopNTFor<Mdl>>(a, src, xfree, gfree, stage_sm, lane, tm);
@@ -1611,13 +1671,23 @@ size_t crl_solve_workspace_bytes(const crl_problem_t* prob, const crl_solver_opt
     return kCtlBytes + queue_bytes(slots) + slots * (size_t)reals * elem;
 }
 
-int crl_solve(const crl_problem_t* prob, const crl_solver_opts_t* opts, const void* x0, const void* u0,
-              int64_t u0_stride_b, const double* J_init, void* X, double* J, int32_t* iters, uint8_t* converged,
-              double* J_trace, int8_t* alpha_trace, void* workspace, size_t workspace_bytes, crl_stream_t stream) {
+static int solve_impl(const crl_problem_t* prob, const crl_solver_opts_t* opts, int n_stage, int32_t* stage_iters,
+                      const void* x0, const void* u0, int64_t u0_stride_b, const double* J_init, void* X, double* J,
+                      int32_t* iters, uint8_t* converged, double* J_trace, int8_t* alpha_trace, void* workspace,
+                      size_t workspace_bytes, crl_stream_t stream) {
     int st = check_problem(prob);
     if (st) return st;
     st = check_opts(opts);
     if (st) return st;
+    if (n_stage > 1) {
+        // one parameter row per stage, constant over the horizon; barrier models only; no per-iteration traces
+        const bool barrier = prob->model == CRL_TWO_LINK_BARRIER || prob->model == CRL_THREE_LINK_BARRIER ||
+                             prob->model == CRL_ROBOTIC_ARM_BARRIER;
+        if (!barrier) return CRL_ERR_UNSUPPORTED_MODEL;
+        if (n_stage >= 128 || opts->max_iter > kStageItMask || prob->params_stride_t != 0 || J_trace || alpha_trace)
+            return CRL_ERR_BAD_ARGUMENT;
+        if (prob->batch > 0 && !stage_iters) return CRL_ERR_BAD_ARGUMENT;
+    }
     if (prob->batch == 0) return CRL_OK;
     if (!x0 || !J || !iters || !converged || !workspace) return CRL_ERR_BAD_ARGUMENT;
     if (opts->max_iter < 1) return CRL_ERR_BAD_ARGUMENT;
@@ -1657,9 +1727,27 @@ int crl_solve(const crl_problem_t* prob, const crl_solver_opts_t* opts, const vo
         a.ws = (R*)((char*)workspace + kCtlBytes + qbytes);
         a.coop_threshold = coop_threshold_for<Mdl, R>(opts, prob->horizon);
         a.slot_elems = slot_elems;
+        a.n_stage = n_stage;
+        a.stage_iters = stage_iters;
         solve_launch<Mdl, R>(effective_variant<Mdl, R>(prob, opts), grid, s, a);
     });
     return cuda_status(cudaGetLastError());
+}
+
+int crl_solve(const crl_problem_t* prob, const crl_solver_opts_t* opts, const void* x0, const void* u0,
+              int64_t u0_stride_b, const double* J_init, void* X, double* J, int32_t* iters, uint8_t* converged,
+              double* J_trace, int8_t* alpha_trace, void* workspace, size_t workspace_bytes, crl_stream_t stream) {
+    return solve_impl(prob, opts, 1, nullptr, x0, u0, u0_stride_b, J_init, X, J, iters, converged, J_trace, alpha_trace,
+                      workspace, workspace_bytes, stream);
+}
+
+int crl_solve_stages(const crl_problem_t* prob, const crl_solver_opts_t* opts, int32_t n_stages, const void* x0,
+                     const void* u0, int64_t u0_stride_b, const double* J_init, void* X, double* J, int32_t* iters,
+                     uint8_t* converged, int32_t* stage_iters, void* workspace, size_t workspace_bytes,
+                     crl_stream_t stream) {
+    if (n_stages < 1) return CRL_ERR_BAD_ARGUMENT;
+    return solve_impl(prob, opts, n_stages, stage_iters, x0, u0, u0_stride_b, J_init, X, J, iters, converged, nullptr,
+                      nullptr, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

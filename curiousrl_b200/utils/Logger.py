@@ -43,6 +43,7 @@ class Logger:
         self.IS_SAVE_JSON = False
         self.FOLDER_NAME = datetime.now().strftime("%Y_%m_%d_%H_%M_%S_%f")
         self.memory_json = None
+        self.memory_batch = None
         self._py = logging.getLogger("curiousrl_b200")
         self._py.setLevel(logging.DEBUG)
         self._py.propagate = False
@@ -124,6 +125,26 @@ class Logger:
         if no_iter == -1 and last is not None:
             return json.loads(last)
         raise Exception("The number of iteration exceeds the maximum iteration number!")
+
+    # ------------------------------------------- batched result channel
+    def save_batch(self, meta=None, **arrays):
+        """Batched counterpart of `save_to_json` (utils/result_stream.py): named arrays with a leading batch axis.
+        In memory (default) the record is kept by reference - device tensors stay on the device; with
+        `set_is_save_json(True)` it is appended to the binary stream under logs/<folder>/stream/."""
+        if self.IS_SAVE_JSON:
+            if not self.IS_USE_LOGGER:
+                raise Exception('Logger must be used to save json. Please call "logger.set_is_use_logger(True)".')
+            from .result_stream import ResultStream
+            return ResultStream(self.FOLDER_NAME).append(meta, **arrays)
+        self.memory_batch = dict(arrays, meta=meta or {})
+        return None
+
+    def read_batch(self, folder_name=None, no_iter=-1):
+        """Batched counterpart of `read_from_json`: record `no_iter` (-1 = last) as {name: array}."""
+        if not self.IS_SAVE_JSON and folder_name is None:
+            return self.memory_batch
+        from .result_stream import ResultStream
+        return ResultStream(self.FOLDER_NAME if folder_name is None else folder_name).read(no_iter)
 
     # ------------------------------------------------------------- messages
     def set_level(self, level):

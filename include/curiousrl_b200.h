@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CRL_ABI_VERSION 3
+#define CRL_ABI_VERSION 4
 
 typedef void* crl_stream_t; /* cudaStream_t */
 
@@ -143,6 +143,22 @@ int crl_solve(const crl_problem_t* prob, const crl_solver_opts_t* opts, const vo
               int64_t u0_stride_b, const double* J_init, void* X, double* J, int32_t* iters,
               uint8_t* converged, double* J_trace, int8_t* alpha_trace, void* workspace,
               size_t workspace_bytes, crl_stream_t stream);
+
+/* LogBarrieriLQR.solve for the whole batch in ONE persistent kernel (log_barrier_ilqr.py:108-149): the outer
+ * loop over the barrier parameter t runs per trajectory inside the kernel.  Trajectory b executes one inner
+ * iLQR loop per stage s = 0 .. n_stages-1 with the parameter row params[b][s] (prob->params is
+ * [B][n_stages][p], params_stride_b = n_stages * p or 0 = shared, params_stride_t must be 0); between stages
+ * it keeps its trajectory, restarts the iteration counter (opts->max_iter is per inner loop, :126) and resets
+ * the stored cost to +inf if the loop ended by the stopping criterion (:140-141).  Barrier models only
+ * (CRL_*_BARRIER): row s is (target_x, target_y, t_s, t_{s-1}), t_{-1} = t_0 (the stale value the first
+ * backward pass of a loop still sees).  n_stages = 1 is crl_solve without traces.
+ *  out: as crl_solve (iters = total over the stages; J, converged = the last stage's) +
+ *       stage_iters [B][n_stages] iterations of every inner loop.
+ *  workspace: crl_solve_workspace_bytes() of the same prob / opts.                                    */
+int crl_solve_stages(const crl_problem_t* prob, const crl_solver_opts_t* opts, int32_t n_stages, const void* x0,
+                     const void* u0, int64_t u0_stride_b, const double* J_init, void* X, double* J, int32_t* iters,
+                     uint8_t* converged, int32_t* stage_iters, void* workspace, size_t workspace_bytes,
+                     crl_stream_t stream);
 
 #ifdef __cplusplus
 }

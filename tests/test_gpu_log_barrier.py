@@ -118,9 +118,23 @@ def test_every_scheduling_path_gives_the_same_bits(model, B):
     cooperative engine as the whole solve (the default at this batch size): bit-identical results."""
     from curiousrl_b200.utils.synthetic import synthetic_batch
     x0, tgt = synthetic_batch(model, B, seed=7)
-    ref = make_algo(model, verify=False, occupancy=12, coop_threshold=-1, max_iter=150).solve_batch(x0, tgt)
+    ref = make_algo(model, verify=False, occupancy=12, coop_threshold=-1, max_iter=150).solve_batch(x0, tgt, fused=False)
     assert int(ref.inner_iterations[:, 0].max()) > 40
-    for kw in (dict(), dict(occupancy=12), dict(occupancy=12, coop_threshold=32), dict(occupancy=20), dict(occupancy=21)):
-        res = make_algo(model, verify=False, max_iter=150, **kw).solve_batch(x0, tgt)
+    for kw in (dict(), dict(occupancy=12), dict(occupancy=12, coop_threshold=32), dict(occupancy=20), dict(occupancy=21),
+               dict(occupancy=12, coop_threshold=-1)):
+        for fused in (True, False):
+            res = make_algo(model, verify=False, max_iter=150, **kw).solve_batch(x0, tgt, fused=fused)
+            for f in ("inner_iterations", "iterations", "converged", "obj_fun_value", "trajectory", "real_obj_fun_value"):
+                assert torch.equal(getattr(res, f), getattr(ref, f)), "%s differs with %s fused=%s" % (f, kw, fused)
+
+
+@pytest.mark.parametrize("tag,model", TAGS)
+def test_fused_schedule_equals_one_launch_per_t(golden, tag, model):
+    """crl_solve_stages (the whole barrier schedule inside one persistent kernel) against one crl_solve launch per t:
+    identical bits, also when inner loops end by max_iter (no reset of the stored cost) and without the stopping test."""
+    g = golden(tag)
+    for kw in (dict(), dict(max_iter=3), dict(max_iter=4, is_check_stop=False)):
+        a = make_algo(model, verify=False, **kw).solve_batch(g["batch_x0"], g["batch_target"], fused=True)
+        b = make_algo(model, verify=False, **kw).solve_batch(g["batch_x0"], g["batch_target"], fused=False)
         for f in ("inner_iterations", "iterations", "converged", "obj_fun_value", "trajectory", "real_obj_fun_value"):
-            assert torch.equal(getattr(res, f), getattr(ref, f)), "%s differs with %s" % (f, kw)
+            assert torch.equal(getattr(a, f), getattr(b, f)), "%s differs with %s" % (f, kw)

@@ -11,16 +11,18 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int
 
 from . import build as _build
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MODEL_IDS = {"TwoLinkPlanarManipulator": 0, "ThreeLinkPlanarManipulator": 1, "RoboticArmTracking": 2}
 # the same scenarios under LogBarrieriLQR's cost (include/curiousrl_b200.h: CRL_*_BARRIER); FP64 only
 BARRIER_MODEL_IDS = {name: mid + 3 for name, mid in MODEL_IDS.items()}
+# scenarios with a GENERATED device model (CRL_GEN_*; curiousrl_b200/codegen.py): FP64, bounds compiled in
+GENERIC_MODEL_IDS = {"CartPoleSwingUp1": 6, "CartPoleSwingUp2": 7, "VehicleTracking": 8, "CarParking": 9}
 DTYPE_IDS = {"float64": 0, "float32": 1}
 LINE_SEARCH_IDS = {"vanilla": 0, "feasibility": 1, "none": 2}
 STOPPING_IDS = {"relative": 0, "vanilla": 1}
 
 # every symbol include/curiousrl_b200.h declares (tests check the library exports all of them)
-EXPORTS = ("crl_abi_version", "crl_status_string", "crl_model_dims", "crl_model_default_bounds", "crl_rollout",
+EXPORTS = ("crl_abi_version", "crl_status_string", "crl_model_dims", "crl_model_default_bounds", "crl_model_bounds", "crl_rollout",
            "crl_cost", "crl_derivs", "crl_backward", "crl_backward_dense", "crl_update_traj", "crl_forward_pass",
            "crl_solve_workspace_bytes", "crl_solve", "crl_solve_stages")
 
@@ -49,6 +51,7 @@ def _declare(lib):
     lib.crl_status_string.argtypes = [c_int]
     lib.crl_model_dims.argtypes = [c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]
     lib.crl_model_default_bounds.argtypes = [c_int, POINTER(c_double), POINTER(c_double)]
+    lib.crl_model_bounds.argtypes = [c_int, POINTER(c_double), POINTER(c_double)]
     lib.crl_rollout.argtypes = [P, vp, vp, c_int64, vp, vp, vp]
     lib.crl_cost.argtypes = [P, vp, vp, vp]
     lib.crl_derivs.argtypes = [P, vp, vp, vp, vp, vp]
@@ -106,3 +109,11 @@ def model_default_bounds(model_id: int):
     lo, hi = c_double(), c_double()
     check(load().crl_model_default_bounds(model_id, lo, hi), "crl_model_default_bounds")
     return lo.value, hi.value
+
+
+def model_bounds(model_id: int):
+    """The scenario's box `constr` as a [d, 2] list of (lo, hi) rows."""
+    n, m, _ = model_dims(model_id)
+    lo, hi = (c_double * (n + m))(), (c_double * (n + m))()
+    check(load().crl_model_bounds(model_id, lo, hi), "crl_model_bounds")
+    return [[lo[i], hi[i]] for i in range(n + m)]

@@ -41,9 +41,12 @@ class BatchResult:
 class DeviceModel:
     def __init__(self, model_name: str, T: int, u_lo: float, u_hi: float, dtype: str = "float64", device=None,
                  barrier: bool = False):
-        if model_name not in _native.MODEL_IDS:
+        self.generic = model_name in _native.GENERIC_MODEL_IDS      # generated device model: FP64, bounds compiled in
+        if model_name not in _native.MODEL_IDS and not self.generic:
             raise Exception('Scenario "%s" has no device model in curiousrl_b200 (supported: %s); '
-                            "there is no CPU fallback." % (model_name, ", ".join(_native.MODEL_IDS)))
+                            "there is no CPU fallback." % (model_name, ", ".join(list(_native.MODEL_IDS) + list(_native.GENERIC_MODEL_IDS))))
+        if self.generic and (barrier or dtype != "float64"):
+            raise ValueError('the generated device model of "%s" is compiled for float64 and the plain cost only' % model_name)
         if dtype not in _TORCH_DTYPE:
             raise ValueError("dtype must be 'float64' or 'float32'")
         self.lib = _native.load()
@@ -53,7 +56,8 @@ class DeviceModel:
         if barrier and dtype != "float64":
             raise ValueError("the log-barrier cost is compiled for float64 only")
         self.model_name = model_name
-        self.model_id = (_native.BARRIER_MODEL_IDS if barrier else _native.MODEL_IDS)[model_name]
+        self.model_id = (_native.GENERIC_MODEL_IDS if self.generic else
+                         _native.BARRIER_MODEL_IDS if barrier else _native.MODEL_IDS)[model_name]
         self.n, self.m, self.p = _native.model_dims(self.model_id)
         self.d = self.n + self.m
         self.T = int(T)

@@ -140,8 +140,10 @@ class iLQRWrapper(AlgoWrapper):
 
     def _params_for(self, B: int) -> torch.Tensor:
         """The solver's current add_param ([T, p], reference semantics) as a device tensor shared by B problems."""
-        ap = np.asarray(self._obj_fun._add_param, dtype=np.float64)
-        return self._dev.real(ap).reshape(1, self._dev.T, self._dev.p)
+        ap = self._obj_fun._add_param
+        if ap is None:                                   # scenario without add_param: zeros [T, 1] (ilqr_obj_fun.py:91-92)
+            ap = np.zeros((self._dev.T, self._dev.p))
+        return self._dev.real(np.asarray(ap, dtype=np.float64)).reshape(1, self._dev.T, self._dev.p)
 
     # -- the two passes (ilqr_wrapper.py:176-230) --------------------------------------------
     def forward_pass(self, trajectory, K_matrix, k_vector):
@@ -254,19 +256,56 @@ class BasiciLQR(iLQRWrapper):
             raise Exception('Scenario "' + scenario.name + '" cannot learn with BasiciLQR')
         constr = np.asarray(scenario.constr, dtype=np.float64)
         n = int(scenario.init_state.shape[0])
-        if not (np.all(constr[:n, 0] == -np.inf) and np.all(constr[:n, 1] == np.inf)):
-            raise Exception('Scenario "%s": finite state bounds are not supported by the device models' % scenario.name)
-        if not (np.all(constr[n:, 0] == constr[n, 0]) and np.all(constr[n:, 1] == constr[n, 1])):
-            raise Exception('Scenario "%s": per-action bounds must be identical' % scenario.name)
         T = int(scenario.init_action.shape[0])
-        self._dev = DeviceModel(scenario.name, T, constr[n, 0], constr[n, 1], dtype=self._dtype, device=self._device)
+        if scenario.name in _native.GENERIC_MODEL_IDS:
+            # generated device model: the whole box - state bounds included - is compiled in
+            compiled = np.asarray(_native.model_bounds(_native.GENERIC_MODEL_IDS[scenario.name]), dtype=np.float64)
+            if compiled.shape != constr.shape or not np.array_equal(compiled, constr):
+                raise Exception('Scenario "%s": the device model is generated for constr = %s (is_with_constraints=True); '
+                                "there is no CPU fallback." % (scenario.name, compiled.tolist()))
+            self._dev = DeviceModel(scenario.name, T, 0.0, 0.0, dtype=self._dtype, device=self._device)
+        else:
+            if not (np.all(constr[:n, 0] == -np.inf) and np.all(constr[:n, 1] == np.inf)):
+                raise Exception('Scenario "%s": finite state bounds are not supported by the device models' % scenario.name)
+            if not (np.all(constr[n:, 0] == constr[n, 0]) and np.all(constr[n:, 1] == constr[n, 1])):
+                raise Exception('Scenario "%s": per-action bounds must be identical' % scenario.name)
+            self._dev = DeviceModel(scenario.name, T, constr[n, 0], constr[n, 1], dtype=self._dtype, device=self._device)
         if (self._dev.n, self._dev.m) != (n, int(len(scenario.x_u_var)) - n):
             raise Exception('Scenario "%s" does not have the shape of the device model' % scenario.name)
         self._dynamic_model = iLQRDynamicModel(self._dev, scenario.init_state, scenario.init_action, self)
         self._obj_fun = iLQRObjectiveFunction(self._dev, scenario.add_param, self)
         if self._verify:
-            self._verify_against(scenario)
+            if self._dev.generic:
+                self._verify_generic(scenario)
+            else:
+                self._verify_against(scenario)
         return self
+
+    def _verify_generic(self, scenario):
+        """Generated device model against the scenario's own sympy f and cost: random trajectories inside the box,
+        cost with the scenario's (time-varying) add_param, one closed-loop step with zero gains for the dynamics."""
+        import sympy as sp
+        dev, rng = self._dev, np.random.default_rng(12345)
+        xu = scenario.x_u_var
+        pv = scenario.add_param_var if scenario.add_param_var is not None else sp.symbols("no_use")
+        f_expr = scenario.dynamic_function
+        f = sp.lambdify([xu], f_expr.tolist() if hasattr(f_expr, "tolist") else f_expr, "math")
+        l = sp.lambdify([xu, pv], scenario.obj_fun, "math")
+        constr = np.asarray(scenario.constr, dtype=np.float64)
+        lo, hi = np.maximum(constr[:, 0], -0.5), np.minimum(constr[:, 1], 0.5)
+        P = _np(self._params_for(1))[0]
+        for _ in range(3):
+            X = rng.uniform(lo, hi, (1, dev.T, dev.d))
+            J = float(dev.cost(X, self._params_for(1)).item())
+            J_ref = sum(float(l(X[0, t], P[t] if scenario.add_param_var is not None else 0.0)) for t in range(dev.T))
+            if not np.isclose(J, J_ref, rtol=1e-9):
+                raise Exception('Scenario "%s": obj_fun differs from the device model' % scenario.name)
+            if dev.T > 1:
+                Xn, _ = dev.update_traj(X, np.zeros((1, dev.T, dev.m, dev.n)), np.zeros((1, dev.T, dev.m)), 0.0,
+                                        self._params_for(1))
+                x1 = np.clip(np.asarray(f(X[0, 0]), dtype=np.float64), constr[:dev.n, 0], constr[:dev.n, 1])
+                if not np.allclose(_np(Xn)[0, 1, :dev.n], x1, rtol=1e-9, atol=1e-9):
+                    raise Exception('Scenario "%s": dynamic_function differs from the device model' % scenario.name)
 
     def _verify_against(self, scenario):
         """Evaluate the scenario's own sympy f and cost at random points and compare with the device model."""

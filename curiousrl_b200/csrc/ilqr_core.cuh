@@ -542,6 +542,69 @@ CRL_HD void derivs_dense(const R* xu, const R* p, R* F, R* c, R* C) {
     }
 }
 
+// One step of the dense Riccati recursion (ilqr_wrapper.py:240-255) on row-major Ft [N][D], ct [D], Ct [D][D]:
+// updates V, v in place and writes the gains Kt [M][N], kt [M].  Products accumulate in the order of the
+// reference's BLAS calls (first term a product, the rest FMAs).
+template <int N, int M, class R>
+CRL_HD void dense_riccati_step(const R* Ft, const R* ct, const R* Ct, R (&V)[N][N], R (&v)[N], R* Kt, R* kt) {
+    constexpr int D = N + M;
+    R Mx[D][N], Q[D][D], q[D];
+    for (int i = 0; i < D; ++i)
+        for (int kk = 0; kk < N; ++kk) {
+            R acc = Ft[0 * D + i] * V[0][kk];
+            for (int l = 1; l < N; ++l) acc = fmadd(Ft[l * D + i], V[l][kk], acc);
+            Mx[i][kk] = acc;
+        }
+    for (int i = 0; i < D; ++i) {
+        for (int j = 0; j < D; ++j) {
+            R acc = Mx[i][0] * Ft[0 * D + j];
+            for (int kk = 1; kk < N; ++kk) acc = fmadd(Mx[i][kk], Ft[kk * D + j], acc);
+            Q[i][j] = Ct[i * D + j] + acc;
+        }
+        R acc = Ft[0 * D + i] * v[0];
+        for (int l = 1; l < N; ++l) acc = fmadd(Ft[l * D + i], v[l], acc);
+        q[i] = ct[i] + acc;
+    }
+    R LU[M][M], X[M][N + 1];
+    for (int a = 0; a < M; ++a) {
+        for (int b = 0; b < M; ++b) LU[a][b] = Q[N + a][N + b];
+        for (int j = 0; j < N; ++j) X[a][j] = Q[N + a][j];
+        X[a][N] = q[N + a];
+    }
+    lu_solve<M, N + 1, R>(LU, X);
+    for (int a = 0; a < M; ++a) {
+        for (int j = 0; j < N; ++j) Kt[a * N + j] = -X[a][j];
+        kt[a] = -X[a][N];
+    }
+    R W[N][M];
+    for (int i = 0; i < N; ++i)
+        for (int b = 0; b < M; ++b) {
+            R acc = Kt[0 * N + i] * Q[N + 0][N + b];
+            for (int a = 1; a < M; ++a) acc = fmadd(Kt[a * N + i], Q[N + a][N + b], acc);
+            W[i][b] = acc;
+        }
+    R Vn[N][N], vn[N];
+    for (int i = 0; i < N; ++i) {
+        R t1 = Q[N][i] * kt[0], t2 = Kt[i] * q[N], t3 = W[i][0] * kt[0];
+        for (int a = 1; a < M; ++a) {
+            t1 = fmadd(Q[N + a][i], kt[a], t1);
+            t2 = fmadd(Kt[a * N + i], q[N + a], t2);
+            t3 = fmadd(W[i][a], kt[a], t3);
+        }
+        vn[i] = ((q[i] + t1) + t2) + t3;
+        for (int j = 0; j < N; ++j) {
+            R s1 = Q[N][i] * Kt[j], s2 = Kt[i] * Q[N][j], r = W[i][0] * Kt[j];
+            for (int a = 1; a < M; ++a) {
+                s1 = fmadd(Q[N + a][i], Kt[a * N + j], s1);
+                s2 = fmadd(Kt[a * N + i], Q[N + a][j], s2);
+                r = fmadd(W[i][a], Kt[a * N + j], r);
+            }
+            Vn[i][j] = ((Q[i][j] + s1) + s2) + r;
+        }
+    }
+    for (int i = 0; i < N; ++i) { v[i] = vn[i]; for (int j = 0; j < N; ++j) V[i][j] = Vn[i][j]; }
+}
+
 // Dense Riccati recursion on caller-supplied F [T][N][D], c [T][D], C [T][D][D] (row-major,
 // one trajectory).  The reference's backward_pass(C, c, F) signature; not on the hot path.
 template <int N, int M, class R>
@@ -549,68 +612,9 @@ CRL_HD void backward_dense(const R* F, const R* c, const R* C, int T, R* K, R* k
     constexpr int D = N + M;
     R V[N][N], v[N];
     for (int i = 0; i < N; ++i) { v[i] = R(0); for (int j = 0; j < N; ++j) V[i][j] = R(0); }
-    for (int t = T - 1; t >= 0; --t) {
-        const R* Ft = F + (size_t)t * N * D;
-        const R* ct = c + (size_t)t * D;
-        const R* Ct = C + (size_t)t * D * D;
-        R Mx[D][N], Q[D][D], q[D];
-        for (int i = 0; i < D; ++i)
-            for (int kk = 0; kk < N; ++kk) {
-                R acc = Ft[0 * D + i] * V[0][kk];
-                for (int l = 1; l < N; ++l) acc = fmadd(Ft[l * D + i], V[l][kk], acc);
-                Mx[i][kk] = acc;
-            }
-        for (int i = 0; i < D; ++i) {
-            for (int j = 0; j < D; ++j) {
-                R acc = Mx[i][0] * Ft[0 * D + j];
-                for (int kk = 1; kk < N; ++kk) acc = fmadd(Mx[i][kk], Ft[kk * D + j], acc);
-                Q[i][j] = Ct[i * D + j] + acc;
-            }
-            R acc = Ft[0 * D + i] * v[0];
-            for (int l = 1; l < N; ++l) acc = fmadd(Ft[l * D + i], v[l], acc);
-            q[i] = ct[i] + acc;
-        }
-        R LU[M][M], X[M][N + 1];
-        for (int a = 0; a < M; ++a) {
-            for (int b = 0; b < M; ++b) LU[a][b] = Q[N + a][N + b];
-            for (int j = 0; j < N; ++j) X[a][j] = Q[N + a][j];
-            X[a][N] = q[N + a];
-        }
-        lu_solve<M, N + 1, R>(LU, X);
-        R* Kt = K + (size_t)t * M * N;
-        R* kt = k + (size_t)t * M;
-        for (int a = 0; a < M; ++a) {
-            for (int j = 0; j < N; ++j) Kt[a * N + j] = -X[a][j];
-            kt[a] = -X[a][N];
-        }
-        R W[N][M];
-        for (int i = 0; i < N; ++i)
-            for (int b = 0; b < M; ++b) {
-                R acc = Kt[0 * N + i] * Q[N + 0][N + b];
-                for (int a = 1; a < M; ++a) acc = fmadd(Kt[a * N + i], Q[N + a][N + b], acc);
-                W[i][b] = acc;
-            }
-        R Vn[N][N], vn[N];
-        for (int i = 0; i < N; ++i) {
-            R t1 = Q[N][i] * kt[0], t2 = Kt[i] * q[N], t3 = W[i][0] * kt[0];
-            for (int a = 1; a < M; ++a) {
-                t1 = fmadd(Q[N + a][i], kt[a], t1);
-                t2 = fmadd(Kt[a * N + i], q[N + a], t2);
-                t3 = fmadd(W[i][a], kt[a], t3);
-            }
-            vn[i] = ((q[i] + t1) + t2) + t3;
-            for (int j = 0; j < N; ++j) {
-                R s1 = Q[N][i] * Kt[j], s2 = Kt[i] * Q[N][j], r = W[i][0] * Kt[j];
-                for (int a = 1; a < M; ++a) {
-                    s1 = fmadd(Q[N + a][i], Kt[a * N + j], s1);
-                    s2 = fmadd(Kt[a * N + i], Q[N + a][j], s2);
-                    r = fmadd(W[i][a], Kt[a * N + j], r);
-                }
-                Vn[i][j] = ((Q[i][j] + s1) + s2) + r;
-            }
-        }
-        for (int i = 0; i < N; ++i) { v[i] = vn[i]; for (int j = 0; j < N; ++j) V[i][j] = Vn[i][j]; }
-    }
+    for (int t = T - 1; t >= 0; --t)
+        dense_riccati_step<N, M, R>(F + (size_t)t * N * D, c + (size_t)t * D, C + (size_t)t * D * D, V, v,
+                                    K + (size_t)t * M * N, k + (size_t)t * M);
 }
 
 // Accept / stop logic of one iteration (ilqr_wrapper.py:98-100, 148-174, 204-213).

@@ -23,6 +23,7 @@
 #include "../../include/curiousrl_b200.h"
 #include "ilqr_core.cuh"
 #include "ilqr_coop.cuh"
+#include "ilqr_generic_host.h"
 
 namespace crl {
 
@@ -1280,6 +1281,14 @@ static OptsDev to_dev(const crl_solver_opts_t* o) {
 
 static int check_problem(const crl_problem_t* p) {
     if (!p) return CRL_ERR_BAD_ARGUMENT;
+    if (gen_is_model(p->model)) {                    // generated models: FP64, parameter rows of the model's own width
+        int pw = 0;
+        gen_dims(p->model, nullptr, nullptr, &pw);
+        if (p->dtype != CRL_F64) return CRL_ERR_UNSUPPORTED_MODEL;
+        if (p->batch < 0 || p->horizon < 1 || (p->batch > 0 && !p->params)) return CRL_ERR_BAD_ARGUMENT;
+        if ((p->params_stride_t != 0 && p->params_stride_t != pw) || p->params_stride_b < 0) return CRL_ERR_BAD_ARGUMENT;
+        return CRL_OK;
+    }
     if (p->model < CRL_TWO_LINK || p->model > CRL_ROBOTIC_ARM_BARRIER) return CRL_ERR_UNSUPPORTED_MODEL;
     if (p->dtype != CRL_F64 && p->dtype != CRL_F32) return CRL_ERR_BAD_ARGUMENT;
     if (p->model >= CRL_TWO_LINK_BARRIER && p->dtype != CRL_F64) return CRL_ERR_UNSUPPORTED_MODEL;   // barrier models: FP64 only
@@ -1527,7 +1536,7 @@ int crl_model_dims(int model, int* n, int* m, int* p) {
         case CRL_TWO_LINK_BARRIER: N = TwoLink::N; M = TwoLink::M; P = Barrier<TwoLink>::P; break;
         case CRL_THREE_LINK_BARRIER: N = ThreeLink::N; M = ThreeLink::M; P = Barrier<ThreeLink>::P; break;
         case CRL_ROBOTIC_ARM_BARRIER: N = RoboticArm::N; M = RoboticArm::M; P = Barrier<RoboticArm>::P; break;
-        default: return CRL_ERR_UNSUPPORTED_MODEL;
+        default: return gen_dims(model, n, m, p) == 0 ? CRL_OK : CRL_ERR_UNSUPPORTED_MODEL;
     }
     if (n) *n = N;
     if (m) *m = M;
@@ -1548,6 +1557,21 @@ int crl_model_default_bounds(int model, double* u_lo, double* u_hi) {
     return CRL_OK;
 }
 
+int crl_model_bounds(int model, double* lo, double* hi) {
+    if (gen_is_model(model)) return gen_bounds(model, lo, hi) == 0 ? CRL_OK : CRL_ERR_UNSUPPORTED_MODEL;
+    int n = 0, m = 0;
+    double ulo = 0.0, uhi = 0.0;
+    int st = crl_model_dims(model, &n, &m, nullptr);
+    if (st) return st;
+    st = crl_model_default_bounds(model, &ulo, &uhi);
+    if (st) return st;
+    for (int i = 0; i < n + m; ++i) {
+        if (lo) lo[i] = i < n ? -(double)INFINITY : ulo;
+        if (hi) hi[i] = i < n ? (double)INFINITY : uhi;
+    }
+    return CRL_OK;
+}
+
 int crl_rollout(const crl_problem_t* prob, const void* x0, const void* u0, int64_t u0_stride_b, void* X, double* J,
                 crl_stream_t stream) {
     int st = check_problem(prob);
@@ -1557,6 +1581,7 @@ int crl_rollout(const crl_problem_t* prob, const void* x0, const void* u0, int64
     DeviceScope scope(x0);
     if (scope.status) return scope.status;
     cudaStream_t s = (cudaStream_t)stream;
+    if (gen_is_model(prob->model)) return cuda_status((cudaError_t)gen_launch_rollout(prob, (const double*)x0, (const double*)u0, u0_stride_b, (double*)X, J, s));
     CRL_DISPATCH(prob->model, prob->dtype, (rollout_kernel<Mdl, R><<<blocks_for(prob->batch), kBlock, 0, s>>>(
                                                to_dev<R>(prob), (const R*)x0, (const R*)u0, u0_stride_b, (R*)X, J)));
     return cuda_status(cudaGetLastError());
@@ -1570,6 +1595,7 @@ int crl_cost(const crl_problem_t* prob, const void* X, double* J, crl_stream_t s
     DeviceScope scope(X);
     if (scope.status) return scope.status;
     cudaStream_t s = (cudaStream_t)stream;
+    if (gen_is_model(prob->model)) return cuda_status((cudaError_t)gen_launch_cost(prob, (const double*)X, J, s));
     CRL_DISPATCH(prob->model, prob->dtype,
                  (cost_kernel<Mdl, R><<<blocks_for(prob->batch), kBlock, 0, s>>>(to_dev<R>(prob), (const R*)X, J)));
     return cuda_status(cudaGetLastError());
@@ -1583,6 +1609,7 @@ int crl_derivs(const crl_problem_t* prob, const void* X, void* F, void* c, void*
     DeviceScope scope(X);
     if (scope.status) return scope.status;
     cudaStream_t s = (cudaStream_t)stream;
+    if (gen_is_model(prob->model)) return cuda_status((cudaError_t)gen_launch_derivs(prob, (const double*)X, (double*)F, (double*)c, (double*)C, s));
     CRL_DISPATCH(prob->model, prob->dtype,
                  (derivs_kernel<Mdl, R><<<blocks_for(prob->batch * prob->horizon), kBlock, 0, s>>>(
                      to_dev<R>(prob), (const R*)X, (R*)F, (R*)c, (R*)C)));
@@ -1597,6 +1624,7 @@ int crl_backward(const crl_problem_t* prob, const void* X, void* K, void* k, crl
     DeviceScope scope(X);
     if (scope.status) return scope.status;
     cudaStream_t s = (cudaStream_t)stream;
+    if (gen_is_model(prob->model)) return cuda_status((cudaError_t)gen_launch_backward(prob, (const double*)X, (double*)K, (double*)k, s));
     CRL_DISPATCH(prob->model, prob->dtype, (backward_kernel<Mdl, R><<<blocks_for(prob->batch), kBlock, 0, s>>>(
                                                to_dev<R>(prob), (const R*)X, (R*)K, (R*)k)));
     return cuda_status(cudaGetLastError());
@@ -1605,7 +1633,9 @@ int crl_backward(const crl_problem_t* prob, const void* X, void* K, void* k, crl
 int crl_backward_dense(int32_t n, int32_t m, int32_t dtype, int64_t batch, int32_t horizon, const void* F, const void* c,
                        const void* C, void* K, void* k, crl_stream_t stream) {
     if (batch < 0 || horizon < 1 || (dtype != CRL_F64 && dtype != CRL_F32)) return CRL_ERR_BAD_ARGUMENT;
-    if (!((n == 6 && m == 2) || (n == 8 && m == 3))) return CRL_ERR_UNSUPPORTED_MODEL;
+    if (!((n == 6 && m == 2) || (n == 8 && m == 3) || (n == 4 && m == 1) || (n == 5 && m == 1) || (n == 4 && m == 2)))
+        return CRL_ERR_UNSUPPORTED_MODEL;
+    if (n <= 5 && dtype != CRL_F64) return CRL_ERR_UNSUPPORTED_MODEL;          // generated models: FP64 only
     if (batch == 0) return CRL_OK;
     if (!F || !c || !C || !K || !k) return CRL_ERR_BAD_ARGUMENT;
     DeviceScope scope(F);
@@ -1615,7 +1645,10 @@ int crl_backward_dense(int32_t n, int32_t m, int32_t dtype, int64_t batch, int32
 #define CRL_BD(NN, MM, RR)                                                                                           \
     backward_dense_kernel<NN, MM, RR><<<g, kBlock, 0, s>>>(batch, horizon, (const RR*)F, (const RR*)c, (const RR*)C, \
                                                            (RR*)K, (RR*)k)
-    if (n == 6 && dtype == CRL_F64) CRL_BD(6, 2, double);
+    if (n == 4 && m == 1) CRL_BD(4, 1, double);
+    else if (n == 5) CRL_BD(5, 1, double);
+    else if (n == 4) CRL_BD(4, 2, double);
+    else if (n == 6 && dtype == CRL_F64) CRL_BD(6, 2, double);
     else if (n == 6) CRL_BD(6, 2, float);
     else if (dtype == CRL_F64) CRL_BD(8, 3, double);
     else CRL_BD(8, 3, float);
@@ -1632,6 +1665,7 @@ int crl_update_traj(const crl_problem_t* prob, const void* X, const void* K, con
     DeviceScope scope(X);
     if (scope.status) return scope.status;
     cudaStream_t s = (cudaStream_t)stream;
+    if (gen_is_model(prob->model)) return cuda_status((cudaError_t)gen_launch_update(prob, (const double*)X, (const double*)K, (const double*)k, alpha, (double*)X_new, J_new, s));
     CRL_DISPATCH(prob->model, prob->dtype,
                  (update_traj_kernel<Mdl, R><<<blocks_for(prob->batch), kBlock, 0, s>>>(
                      to_dev<R>(prob), (const R*)X, (const R*)K, (const R*)k, alpha, (R*)X_new, J_new)));
@@ -1650,6 +1684,7 @@ int crl_forward_pass(const crl_problem_t* prob, const crl_solver_opts_t* opts, c
     DeviceScope scope(X);
     if (scope.status) return scope.status;
     cudaStream_t s = (cudaStream_t)stream;
+    if (gen_is_model(prob->model)) return cuda_status((cudaError_t)gen_launch_forward(prob, opts, (const double*)X, (const double*)K, (const double*)k, J_last, (double*)X_new, J_new, alpha_index, stop, s));
     CRL_DISPATCH(prob->model, prob->dtype,
                  (forward_pass_kernel<Mdl, R><<<blocks_for(prob->batch), kBlock, 0, s>>>(
                      to_dev<R>(prob), to_dev(opts), (const R*)X, (const R*)K, (const R*)k, J_last, (R*)X_new, J_new,
@@ -1659,6 +1694,7 @@ int crl_forward_pass(const crl_problem_t* prob, const crl_solver_opts_t* opts, c
 
 size_t crl_solve_workspace_bytes(const crl_problem_t* prob, const crl_solver_opts_t* opts) {
     if (check_problem(prob) || check_opts(opts)) return 0;
+    if (gen_is_model(prob->model)) return gen_solve_workspace_bytes(prob);
     long long reals = 0;
     int grid = 0, warps = 0;
     CRL_DISPATCH(prob->model, prob->dtype,
@@ -1698,6 +1734,9 @@ static int solve_impl(const crl_problem_t* prob, const crl_solver_opts_t* opts, 
     DeviceScope scope(x0);
     if (scope.status) return scope.status;
     cudaStream_t s = (cudaStream_t)stream;
+    if (gen_is_model(prob->model))
+        return cuda_status((cudaError_t)gen_launch_solve(prob, opts, (const double*)x0, (const double*)u0, u0_stride_b, J_init,
+                                                         (double*)X, J, iters, converged, J_trace, alpha_trace, workspace, s));
     size_t qbytes = 0;
     int grid = 0, warps = 0;
     long long slot_elems = 0;

@@ -35,3 +35,11 @@ def synthetic_batch(model_name: str, batch: int, seed: int = 0):
     x0[:, n - 1] = (np.asarray(lengths) * np.cos(ang)).sum(axis=1)
     target = np.stack([r * np.cos(phi), r * np.sin(phi)], axis=1)
     return x0, target
+
+
+def synthetic_init_states(scenario, batch: int, seed: int = 0, spread: float = 0.05):
+    """Seeded batch for the scenarios without a target (cart-pole / vehicle): the scenario's own initial state
+    plus uniform noise of half-width `spread` on every entry, x0 [B, n] float64 (PCG64, one vectorised draw)."""
+    rng = np.random.default_rng(seed)
+    base = np.asarray(scenario.init_state, dtype=np.float64).reshape(1, -1)
+    return base + spread * rng.uniform(-1.0, 1.0, (batch, base.shape[1]))

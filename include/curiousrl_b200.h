@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CRL_ABI_VERSION 4
+#define CRL_ABI_VERSION 5
 
 typedef void* crl_stream_t; /* cudaStream_t */
 
@@ -41,7 +41,15 @@ enum crl_model {              /* scenario.name -> precompiled device model      
        sees (the reference evaluates its cost derivatives before the outer loop moves t on).            */
     CRL_TWO_LINK_BARRIER = 3,
     CRL_THREE_LINK_BARRIER = 4,
-    CRL_ROBOTIC_ARM_BARRIER = 5
+    CRL_ROBOTIC_ARM_BARRIER = 5,
+    /* Scenarios whose device model is GENERATED from the scenario's sympy expressions (curiousrl_b200/codegen.py ->
+       csrc/ilqr_generated.cuh): dense Jacobians, state-dependent cost Hessians, time-varying cost parameters,
+       per-component bounds on states and actions compiled into the model (u_lo / u_hi of crl_problem are ignored;
+       crl_model_bounds reports them).  FP64 only.  Every entry point below accepts them.                  */
+    CRL_GEN_CART_POLE_1 = 6,       /* CartPoleSwingUp1  cart_pole_swingup1.py:16   n=4 m=1 p=5 */
+    CRL_GEN_CART_POLE_2 = 7,       /* CartPoleSwingUp2  cart_pole_swingup2.py:16   n=5 m=1 p=6 */
+    CRL_GEN_VEHICLE_TRACKING = 8,  /* VehicleTracking   vehicle_tracking.py:15     n=4 m=2 p=1 (one unused zero column) */
+    CRL_GEN_CAR_PARKING = 9        /* CarParking        car_parking.py:23          n=4 m=2 p=2 */
 };
 enum crl_dtype { CRL_F64 = 0, CRL_F32 = 1 };
 enum crl_line_search { CRL_LS_VANILLA = 0, CRL_LS_FEASIBILITY = 1, CRL_LS_NONE = 2 }; /* ilqr_wrapper.py:74-146 */
@@ -94,6 +102,9 @@ const char* crl_status_string(int status);
 int crl_model_dims(int model, int* n, int* m, int* p);
 /* Default action box of the scenario class (u in [-100,100] / [-500,500]).                      */
 int crl_model_default_bounds(int model, double* u_lo, double* u_hi);
+/* The box `constr` of a scenario, component by component: lo / hi receive d = n + m entries (states first).
+ * For the arm models the states are unbounded and every action has the default box.               */
+int crl_model_bounds(int model, double* lo, double* hi);
 
 /* iLQRDynamicModel.eval_traj + iLQRObjectiveFunction.eval_obj_fun
  * (ilqr_dynamic_model.py:39-54,96-109; ilqr_obj_fun.py:54-62,86-95).

@@ -68,9 +68,14 @@ class Problem:
         self.constr = np.asarray(scenario.constr, dtype=np.float64)
         self.init_state = np.asarray(scenario.init_state, dtype=np.float64).reshape(-1)
         self.init_action = np.asarray(scenario.init_action, dtype=np.float64).reshape(self.T, self.m)
-        self.add_param = np.asarray(scenario.add_param, dtype=np.float64)
-        pv = scenario.add_param_var
         unused = sp.symbols("no_use")
+        pv = scenario.add_param_var
+        if pv is None:                                   # ilqr_obj_fun.py:44-45
+            pv = unused
+        if scenario.add_param is None:                   # ilqr_obj_fun.py:91-92 (and :103-104, :115-116)
+            self.add_param = np.zeros((self.T, 1))
+        else:
+            self.add_param = np.asarray(scenario.add_param, dtype=np.float64)
         f_sym = scenario.dynamic_function
         # ilqr_dynamic_model.py:33-35 - dynamics never see add_param
         f = _lambdify([xu, unused], f_sym, "math")
@@ -125,7 +130,7 @@ def _update_traj(f, X, K, k, alpha, n, m, constr):
     Xn[0] = X[0]
     for t in range(T - 1):
         dx = Xn[t, :n] - X[t, :n]
-        du = K[t] @ dx + alpha * k[t]
+        du = (K[t] @ dx.reshape(n, 1)).reshape(m) + alpha * k[t]     # 2-D @ 2-D like the reference (:123): BLAS dgemm, not dgemv
         Xn[t, n:] = X[t, n:] + du
         for i in range(m):                                              # action clamp before dynamics
             Xn[t, n + i] = min(max(constr[n + i, 0], Xn[t, n + i]), constr[n + i, 1])

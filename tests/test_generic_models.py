@@ -1,0 +1,123 @@
+"""Generated device models without a GPU.
+
+* the oracle (oracle/ilqr_numpy.py on the numba substrate, like the reference) is pinned BIT-EXACTLY to golden vectors of
+  the unmodified reference for CartPoleSwingUp1/2, VehicleTracking and CarParking (tests/golden/Generic_*.npz, written by
+  oracle/make_golden_generic.py with BasiciLQR(max_line_search=10, max_iter=100));
+* the generated CUDA header is up to date with the generator and the scenario classes;
+* the device math (csrc/ilqr_generic.cuh over csrc/ilqr_generated.cuh, compiled for the host by tests/hostsim) reproduces
+  the reference stage by stage (<= 1e-12 relative; its libm calls and pow() are not the reference's bit for bit) and end
+  to end: same iteration count, same accepted steps, cost <= 1e-9 relative (the CarParking problem is reproducible by the
+  reference itself only to 4e-9 under 1e-15 noise on K, k - fixture `default_noise_Xerr`).
+"""
+import numpy as np
+import pytest
+
+from conftest import make_scenario
+from hostsim.generic import GenericHostSim
+from oracle import ilqr_numpy as orc
+
+TAGS = ["Generic_CartPole1_T150", "Generic_CartPole2_T150", "Generic_Vehicle_T150", "Generic_CarParking_T500",
+        "Generic_Vehicle_T40"]
+_PROBS = {}
+
+
+def _prob(g):
+    key = (str(g["model"]), int(g["T"]))
+    if key not in _PROBS:
+        _PROBS[key] = orc.Problem(make_scenario(*key), use_numba=True)
+    return _PROBS[key]
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.nanmax(np.abs(a - b)) / max(1e-300, np.nanmax(np.abs(b))))
+
+
+@pytest.mark.parametrize("tag", TAGS[2:])
+def test_oracle_is_bit_exact_on_the_reference_vectors(golden, tag):
+    g = golden(tag)
+    prob = _prob(g)
+    P = prob.params()
+    assert np.array_equal(orc.rollout(prob, g["default_x0"]), g["default_X_init"])
+    for it in g["stage_iters"]:
+        pre = "stage%d_" % it
+        X = g[pre + "X"]
+        F, c, C = orc.derivs(prob, X, P)
+        assert np.array_equal(F, g[pre + "F"]) and np.array_equal(c, g[pre + "c"]) and np.array_equal(C, g[pre + "C"])
+        K, k = orc.backward(prob, F, c, C)
+        assert np.array_equal(K, g[pre + "K"]) and np.array_equal(k, g[pre + "k"])
+        for alpha, Xc, Jc in zip(g[pre + "cand_alpha"], g[pre + "cand_X"], g[pre + "cand_J"]):
+            Xn = orc.update_traj(prob, X, K, k, alpha)
+            assert np.array_equal(Xn, Xc, equal_nan=True)
+            Jn = orc.cost(prob, Xn, P)
+            assert Jn == Jc or (np.isnan(Jn) and np.isnan(Jc))
+    r = orc.solve(prob, g["default_x0"], None, max_line_search=int(g["max_line_search"]), max_iter=int(g["max_iter"]))
+    assert r["iters"] == int(g["default_iters"])
+    assert np.array_equal(r["Js"], g["default_Js"]) and np.array_equal(r["alphas"], g["default_alphas"])
+    assert np.array_equal(r["X"], g["default_X"])
+
+
+@pytest.mark.parametrize("tag", TAGS[:2])
+def test_oracle_end_to_end_on_the_cart_poles(golden, tag):
+    g = golden(tag)
+    prob = _prob(g)
+    r = orc.solve(prob, g["default_x0"], None, max_line_search=int(g["max_line_search"]), max_iter=int(g["max_iter"]))
+    assert r["iters"] == int(g["default_iters"])
+    assert np.array_equal(r["Js"], g["default_Js"]) and np.array_equal(r["alphas"], g["default_alphas"])
+    assert np.array_equal(r["X"], g["default_X"])
+    b = 1
+    r = orc.solve(prob, g["batch_x0"][b], None, max_line_search=int(g["max_line_search"]), max_iter=int(g["max_iter"]))
+    assert r["iters"] == int(g["batch_iters"][b]) and r["J"] == float(g["batch_J"][b])
+
+
+def test_generated_header_is_current():
+    """csrc/ilqr_generated.cuh is what the generator prints from the scenario classes today."""
+    from curiousrl_b200 import codegen
+    with open(codegen.HEADER_PATH) as fh:
+        assert fh.read() == codegen.generate_header(codegen.default_scenarios())
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_device_math_stage_by_stage(golden, tag):
+    g = golden(tag)
+    sc = make_scenario(str(g["model"]), int(g["T"]))
+    hs = GenericHostSim(str(g["model"]))
+    assert (hs.n, hs.m) == (int(g["n"]), int(g["m"]))
+    assert np.array_equal(hs.bounds(), np.asarray(sc.constr, dtype=np.float64))
+    P, T = sc.add_param, int(g["T"])
+    X0, _ = hs.rollout(g["default_x0"], P, T)
+    assert rel(X0, g["default_X_init"]) <= 1e-13
+    for it in g["stage_iters"]:
+        pre = "stage%d_" % it
+        X = g[pre + "X"]
+        F, c, C = hs.derivs(X, P)
+        assert rel(F, g[pre + "F"]) <= 1e-13 and rel(c, g[pre + "c"]) <= 1e-13 and rel(C, g[pre + "C"]) <= 1e-13
+        K, k = hs.backward(X, P)
+        assert rel(K, g[pre + "K"]) <= 1e-11 and rel(k, g[pre + "k"]) <= 1e-11
+        for alpha, Xc, Jc in zip(g[pre + "cand_alpha"], g[pre + "cand_X"], g[pre + "cand_J"]):
+            Xn, Jn = hs.update(X, g[pre + "K"], g[pre + "k"], alpha, P)
+            if np.isnan(Jc):
+                assert np.isnan(Jn)                       # sqrt of a negative number in the vehicle model: rejected
+                continue
+            assert rel(Xn, Xc) <= 1e-12 and abs(Jn - Jc) <= 1e-12 * abs(Jc)
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_device_math_end_to_end(golden, tag):
+    g = golden(tag)
+    sc = make_scenario(str(g["model"]), int(g["T"]))
+    hs = GenericHostSim(str(g["model"]))
+    kw = dict(max_iter=int(g["max_iter"]), max_line_search=int(g["max_line_search"]))
+    r = hs.solve(g["default_x0"], sc.add_param, int(g["T"]), **kw)
+    assert r["iters"] == int(g["default_iters"]) and np.array_equal(r["alphas"], g["default_alphas"])
+    assert abs(r["J"] - float(g["default_J"])) <= 1e-9 * abs(float(g["default_J"]))
+    tol = max(1e-9, 100.0 * float(g["default_noise_Xerr"].max()))
+    assert rel(r["X"], g["default_X"]) <= tol
+    # seeded batch: same iteration count; cost within 1e-9, or - where the reference itself moves under 1e-15 noise on
+    # K, k (CarParking: up to 0.4 % of J) - within 4x the reference's own spread
+    spread = np.abs(g["noise_J"] - g["batch_J"][:, None]).max(axis=1) / np.abs(g["batch_J"])
+    same_iters = np.all(g["noise_iters"] == g["batch_iters"][:, None], axis=1)
+    for b in np.flatnonzero(same_iters)[:3]:
+        r = hs.solve(g["batch_x0"][b], sc.add_param, int(g["T"]), **kw)
+        assert r["iters"] == int(g["batch_iters"][b])
+        assert abs(r["J"] - float(g["batch_J"][b])) <= max(1e-9, 4.0 * spread[b]) * abs(float(g["batch_J"][b]))

@@ -1,0 +1,135 @@
+"""Generated device models on the B200 through the C ABI: CartPoleSwingUp1/2,
+VehicleTracking, CarParking against golden vectors of the unmodified reference (tests/golden/Generic_*.npz,
+BasiciLQR(max_line_search=10, max_iter=100)).
+
+Tolerances (FP64): stage tensors <= 1e-12 relative (gains 1e-10); end to end the SAME iteration count and accepted-step
+sequence, final cost <= 1e-9 relative, trajectory within the larger of 1e-8 and 100x the reference's own
+reproducibility under 1e-15 noise on K, k (fixture `default_noise_Xerr`; CarParking reproduces itself to 4e-9 only).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_scenario
+
+pytestmark = pytest.mark.gpu
+
+TAGS = ["Generic_CartPole1_T150", "Generic_CartPole2_T150", "Generic_Vehicle_T150", "Generic_CarParking_T500",
+        "Generic_Vehicle_T40"]
+
+
+def make_algo(g, **kw):
+    from curiousrl_b200 import logger
+    from curiousrl_b200.algorithm.ilqr_solver import BasiciLQR
+    logger.set_level(45)
+    kw.setdefault("max_line_search", int(g["max_line_search"]))
+    kw.setdefault("max_iter", int(g["max_iter"]))
+    return BasiciLQR(**kw).init(make_scenario(str(g["model"]), int(g["T"])))
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.nanmax(np.abs(a - b)) / max(1e-300, np.nanmax(np.abs(b))))
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_stage_parity(golden, tag):
+    """The reference's per-stage methods (eval_traj, eval_obj_fun, eval_grad_*, backward_pass, update_traj, forward_pass)."""
+    g = golden(tag)
+    algo = make_algo(g)
+    n = algo.dynamic_model.n
+    assert rel(algo.dynamic_model.eval_traj()[:, :, 0], g["default_X_init"]) <= 1e-13
+    for it in g["stage_iters"]:
+        pre = "stage%d_" % it
+        X = g[pre + "X"][:, :, None]
+        assert rel(algo.dynamic_model.eval_grad_dynamic_model(X), g[pre + "F"]) <= 1e-12
+        assert rel(algo.obj_fun.eval_grad_obj_fun(X)[:, :, 0], g[pre + "c"]) <= 1e-12
+        assert rel(algo.obj_fun.eval_hessian_obj_fun(X), g[pre + "C"]) <= 1e-12
+        K, k = algo.backward_pass(g[pre + "C"], g[pre + "c"][:, :, None], g[pre + "F"])
+        assert rel(K, g[pre + "K"]) <= 1e-10 and rel(k[:, :, 0], g[pre + "k"]) <= 1e-10
+        Kf, kf = algo._dev.backward(g[pre + "X"][None], algo._params_for(1))        # derivatives recomputed on chip
+        assert rel(Kf.cpu().numpy()[0], g[pre + "K"]) <= 1e-10 and rel(kf.cpu().numpy()[0], g[pre + "k"]) <= 1e-10
+        for alpha, Xc, Jc in zip(g[pre + "cand_alpha"], g[pre + "cand_X"], g[pre + "cand_J"]):
+            Xn = algo.dynamic_model.update_traj(X, g[pre + "K"], g[pre + "k"][:, :, None], alpha)
+            Jn = algo.obj_fun.eval_obj_fun(Xn)
+            if np.isnan(Jc):
+                assert np.isnan(Jn)
+                continue
+            assert rel(Xn[:, :, 0], Xc) <= 1e-12 and abs(Jn - Jc) <= 1e-12 * abs(Jc)
+        algo.set_obj_fun_value(float(g[pre + "J_last"]))
+        out = algo.forward_pass(X, g[pre + "K"], g[pre + "k"][:, :, None])
+        assert rel(out[0][:, :, 0], g[pre + "X_next"]) <= 1e-12
+        assert abs(out[4] - float(g[pre + "J_next"])) <= 1e-12 * abs(float(g[pre + "J_next"]))
+        assert out[5] == bool(g[pre + "stop"])
+        assert out[0].shape == (int(g["T"]), n + algo.dynamic_model.m, 1)
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_default_problem_solve(golden, tag):
+    """solve(): reference semantics for one problem (returns None, trajectory on the JSON channel)."""
+    from curiousrl_b200 import logger
+    g = golden(tag)
+    algo = make_algo(g)
+    assert algo.solve() is None
+    res = algo.last_result.to_host()
+    it = int(g["default_iters"])
+    assert int(res.iterations[0]) == it
+    assert np.array_equal(res.alpha_trace[0, :it], g["default_alphas"])
+    assert np.allclose(res.obj_fun_trace[0, :it], g["default_Js"], rtol=1e-9, atol=0)
+    assert abs(algo.get_obj_fun_value() - float(g["default_J"])) <= 1e-9 * abs(float(g["default_J"]))
+    tol = max(1e-8, 100.0 * float(g["default_noise_Xerr"].max()))
+    assert rel(algo._trajectory[:, :, 0], g["default_X"]) <= tol
+    assert np.asarray(logger.read_from_json()["trajectory"]).shape == (int(g["T"]), algo._dev.d, 1)
+    # bounds hold on every stored row but the last (never clamped, ilqr_dynamic_model.py:104-108)
+    constr = np.asarray(make_scenario(str(g["model"]), int(g["T"])).constr, dtype=np.float64)
+    X = algo._trajectory[:-1, :, 0]
+    assert np.all(X >= constr[:, 0] - 1e-12) and np.all(X <= constr[:, 1] + 1e-12)
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_seeded_batch(golden, tag):
+    g = golden(tag)
+    algo = make_algo(g)
+    res = algo.solve_batch(g["batch_x0"], trace=True).to_host()
+    spread = np.abs(g["noise_J"] - g["batch_J"][:, None]).max(axis=1) / np.abs(g["batch_J"])
+    same_iters = np.all(g["noise_iters"] == g["batch_iters"][:, None], axis=1)
+    assert same_iters.sum() >= 0.7 * len(same_iters)
+    for b in np.flatnonzero(same_iters):
+        it = int(g["batch_iters"][b])
+        assert int(res.iterations[b]) == it
+        assert np.array_equal(res.alpha_trace[b, :it], g["batch_alphas"][b, :it])
+        assert abs(res.obj_fun_value[b] - g["batch_J"][b]) <= max(1e-9, 4.0 * spread[b]) * abs(g["batch_J"][b])
+        if spread[b] <= 1e-10:
+            assert rel(res.trajectory[b], g["batch_X"][b]) <= max(1e-8, 100.0 * float(g["noise_Xerr"][b].max()))
+
+
+def test_large_batch_properties():
+    """Size-independent checks on a batch that spans many warps (ragged last warp): every problem equals its own
+    single-problem solve bit for bit, costs re-evaluate to the reported value, iteration counts respect max_iter."""
+    from curiousrl_b200.utils.synthetic import synthetic_init_states
+    sc = make_scenario("VehicleTracking", 40)
+    from curiousrl_b200 import logger
+    from curiousrl_b200.algorithm.ilqr_solver import BasiciLQR
+    logger.set_level(45)
+    algo = BasiciLQR(max_line_search=10, max_iter=30).init(sc)
+    B = 4133
+    x0 = synthetic_init_states(sc, B, seed=5, spread=0.2)
+    res = algo.solve_batch(x0)
+    J = algo.obj_fun.eval_obj_fun(res.trajectory)
+    assert torch.equal(J, res.obj_fun_value)
+    assert int(res.iterations.max()) <= 30 and int(res.iterations.min()) >= 1
+    for b in (0, 31, 32, 4100, B - 1):
+        one = algo.solve_batch(x0[b:b + 1])
+        assert torch.equal(one.trajectory[0], res.trajectory[b]) and int(one.iterations[0]) == int(res.iterations[b])
+    assert torch.equal(res.trajectory[:, -1, 4:], torch.zeros_like(res.trajectory[:, -1, 4:]))     # last action stays 0
+
+
+def test_unconstrained_variant_and_other_solvers_raise():
+    import curiousrl_b200.scenario.dynamic_model as models
+    from curiousrl_b200.algorithm.ilqr_solver import BasiciLQR, LogBarrieriLQR
+    with pytest.raises(Exception, match="generated for constr"):
+        BasiciLQR().init(models.VehicleTracking(is_with_constraints=False, T=20))
+    with pytest.raises(Exception):
+        LogBarrieriLQR().init(models.VehicleTracking(T=20))
+    with pytest.raises(Exception):
+        BasiciLQR(dtype="float32").init(models.VehicleTracking(T=20))

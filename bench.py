@@ -127,6 +127,16 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(rows)}
 
 
+def bench_inputs(model, batch, seed, T):
+    """(x0 [B, n], targets [B, 2] or None): the arm scenarios draw random states and targets; the
+    scenarios with a generated device model (cart-pole, vehicle: no target) perturb their own initial state."""
+    from curiousrl_b200.utils.synthetic import ARM_GEOMETRY, synthetic_batch, synthetic_init_states
+    if model in ARM_GEOMETRY:
+        return synthetic_batch(model, batch, seed=seed)
+    import curiousrl_b200.scenario.dynamic_model as models
+    return synthetic_init_states(getattr(models, model)(T=T), batch, seed=seed), None
+
+
 # ----------------------------------------------------------------------------- CPU baseline (oracle port)
 _WORKER = {}
 
@@ -139,11 +149,11 @@ def _cpu_init(model, T, barrier, solver="basic"):
     import warnings
     warnings.filterwarnings("ignore")
     import curiousrl_b200.scenario.dynamic_model as models
-    from curiousrl_b200.utils.synthetic import synthetic_batch
     from oracle import ilqr_numpy as orc                 # CPU baseline / reference arm: the one place bench.py runs the oracle
     sc = getattr(models, model)(T=T)
     prob = orc.Problem(sc, use_numba=True)
-    x0, tgt = synthetic_batch(model, 1, seed=99)
+    x0, tgt = bench_inputs(model, 1, 99, T)
+    tgt = [None] if tgt is None else tgt
     orc.solve(prob, x0[0], tgt[0], max_line_search=MAX_LINE_SEARCH, max_iter=3)
     _WORKER["prob"], _WORKER["orc"], _WORKER["barrier"], _WORKER["prob_barrier"] = prob, orc, barrier, None
     if solver == "logbarrier":
@@ -160,7 +170,7 @@ def _cpu_solve(job):
     pb = _WORKER["prob_barrier"]
     for b in range(x0.shape[0]):
         if pb is None:
-            iters += orc.solve(prob, x0[b], tgt[b], max_line_search=MAX_LINE_SEARCH)["iters"]
+            iters += orc.solve(prob, x0[b], None if tgt is None else tgt[b], max_line_search=MAX_LINE_SEARCH)["iters"]
         else:
             iters += int(orc.solve_log_barrier(pb, prob, x0[b], tgt[b], max_line_search=MAX_LINE_SEARCH)["inner_iters"].sum())
     return iters, time.perf_counter() - t0
@@ -171,7 +181,7 @@ class CpuReference:
 
     def __init__(self, model, T, cores=None, solver="basic"):
         import multiprocessing as mp
-        self.model = model
+        self.model, self.T = model, T
         self.cores = cores or min(os.cpu_count() or 1, 64)
         ctx = mp.get_context("spawn")
         self.pool = ctx.Pool(self.cores, initializer=_cpu_init, initargs=(model, T, ctx.Barrier(self.cores), solver))
@@ -179,9 +189,8 @@ class CpuReference:
 
     def run(self, per_core, seed):
         """Solve the first per_core*cores trajectories of the seeded batch; returns (iters, seconds)."""
-        from curiousrl_b200.utils.synthetic import synthetic_batch
-        x0, tgt = synthetic_batch(self.model, per_core * self.cores, seed=seed)
-        jobs = [(x0[c::self.cores], tgt[c::self.cores]) for c in range(self.cores)]
+        x0, tgt = bench_inputs(self.model, per_core * self.cores, seed, self.T)
+        jobs = [(x0[c::self.cores], None if tgt is None else tgt[c::self.cores]) for c in range(self.cores)]
         t0 = time.perf_counter()
         out = self.pool.map(_cpu_solve, jobs, chunksize=1)
         wall = time.perf_counter() - t0
@@ -244,7 +253,6 @@ def run_b200(args):
     from curiousrl_b200.algorithm.ilqr_solver import BasiciLQR, LogBarrieriLQR
     from curiousrl_b200.distributed import gather_results
     import curiousrl_b200.scenario.dynamic_model as models
-    from curiousrl_b200.utils.synthetic import synthetic_batch
 
     logger.set_level(45)
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -268,11 +276,11 @@ def run_b200(args):
     else:
         algo = BasiciLQR(**kw).init(getattr(models, args.model)(T=T))
     dm = algo._dev
-    x0_h, tgt_h = synthetic_batch(args.model, B, seed=1234 + rank)
+    x0_h, tgt_h = bench_inputs(args.model, B, 1234 + rank, T)
     np_dt = np.float64 if args.dtype == "float64" else np.float32
     x0_pin = torch.from_numpy(x0_h.astype(np_dt)).pin_memory()
-    tgt_pin = torch.from_numpy(tgt_h.astype(np_dt)).pin_memory()
-    x0_d, tgt_d = x0_pin.to(dev), tgt_pin.to(dev)
+    tgt_pin = None if tgt_h is None else torch.from_numpy(tgt_h.astype(np_dt)).pin_memory()     # None: the scenario's own add_param
+    x0_d, tgt_d = x0_pin.to(dev), (None if tgt_pin is None else tgt_pin.to(dev))
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     out = None
     total_B = B * world
@@ -331,10 +339,11 @@ def run_b200(args):
     X_h = torch.empty((B, T, dm.d), dtype=dm.dtype).pin_memory()
 
     def step_e2e():
+        tgt_in = None if tgt_pin is None else tgt_pin.to(dev, non_blocking=True)
         if args.solver == "basic":
-            r = algo.solve_batch(x0_pin.to(dev, non_blocking=True), tgt_pin.to(dev, non_blocking=True), out=out)
+            r = algo.solve_batch(x0_pin.to(dev, non_blocking=True), tgt_in, out=out)
         else:
-            r = algo.solve_batch(x0_pin.to(dev, non_blocking=True), tgt_pin.to(dev, non_blocking=True))
+            r = algo.solve_batch(x0_pin.to(dev, non_blocking=True), tgt_in)
         if world > 1:
             gather_results(r.obj_fun_value, r.iterations, r.converged, total_B)
         J_h.copy_(r.obj_fun_value, non_blocking=True)
@@ -355,7 +364,7 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = iters_all / float(e2e_t[0])
-    h2d = x0_pin.numel() * x0_pin.element_size() + tgt_pin.numel() * tgt_pin.element_size()
+    h2d = x0_pin.numel() * x0_pin.element_size() + (0 if tgt_pin is None else tgt_pin.numel() * tgt_pin.element_size())
     d2h = sum(t.numel() * t.element_size() for t in (J_h, it_h, cv_h, X_h))
 
     if rank != 0:
@@ -378,7 +387,8 @@ def run_b200(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3},
-            "roofline": {"bound": "hbm", "kernel": "solve_kernel<%s,%s>" % (args.model, args.dtype), "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "%s<%s,%s>" % ("gen_solve_kernel" if dm.generic else "solve_kernel", args.model, args.dtype),
+                         "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_traj_iter": bpi,
                          "algorithmic_bytes_per_launch": iters_local * bpi}}

@@ -61,7 +61,7 @@ def test_solver_constructor_and_accessors_without_gpu():
 def test_unsupported_scenario_raises_instead_of_falling_back():
     from curiousrl_b200.algorithm.ilqr_solver import DeviceModel
     with pytest.raises(Exception, match="no device model"):
-        DeviceModel("CartPoleSwingUp1", 100, -1.0, 1.0)
+        DeviceModel("TwoWheeledRobot", 100, -1.0, 1.0)
 
 
 def test_logger_result_channel(tmp_path, monkeypatch):

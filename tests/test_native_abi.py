@@ -35,11 +35,19 @@ def test_model_tables_and_status_strings():
     assert _native.model_dims(3) == (6, 2, 4) and _native.model_dims(4) == (8, 3, 4) and _native.model_dims(5) == (6, 2, 4)
     assert _native.model_default_bounds(5) == (-500.0, 500.0)
     lib = _native.load()
-    assert lib.crl_model_dims(7, None, None, None) == -2
+    assert lib.crl_model_dims(10, None, None, None) == -2
     assert b"unsupported model" in lib.crl_status_string(-2)
     assert lib.crl_status_string(0) == b"ok"
     with pytest.raises(RuntimeError, match="unsupported model"):
         _native.model_dims(99)
+    # generated device models (CRL_GEN_*): sizes and the compiled-in box equal the scenario classes'
+    import curiousrl_b200.scenario.dynamic_model as models
+    for name, mid in _native.GENERIC_MODEL_IDS.items():
+        sc = getattr(models, name)(T=5)
+        p = 1 if sc.add_param is None else sc.add_param.shape[1]
+        assert _native.model_dims(mid) == (sc.n, sc.m, p)
+        assert np.array_equal(np.asarray(_native.model_bounds(mid)), np.asarray(sc.constr, dtype=np.float64))
+    assert _native.model_bounds(1) == [[-np.inf, np.inf]] * 8 + [[-100.0, 100.0]] * 3
 
 
 def test_argument_validation_happens_before_any_cuda_call():
@@ -58,7 +66,9 @@ def test_argument_validation_happens_before_any_cuda_call():
     opts = _native.SolverOpts(10, 1, 1e-6, 10, 0.5, 0, 0, 0, 0, 0, 0)
     dummy = ctypes.c_void_p(0x1000)
     assert lib.crl_rollout(None, dummy, None, 0, dummy, None, None) == -1
-    assert lib.crl_rollout(prob(model=6), dummy, None, 0, dummy, None, None) == -2
+    assert lib.crl_rollout(prob(model=10), dummy, None, 0, dummy, None, None) == -2
+    assert lib.crl_rollout(prob(model=6, dtype=1), dummy, None, 0, dummy, None, None) == -2   # generated models are FP64 only
+    assert lib.crl_rollout(prob(model=6, params_stride_t=2), dummy, None, 0, dummy, None, None) == -1   # its rows are 5 wide
     assert lib.crl_rollout(prob(model=5, dtype=1), dummy, None, 0, dummy, None, None) == -2   # barrier models are FP64 only
     assert lib.crl_rollout(prob(dtype=3), dummy, None, 0, dummy, None, None) == -1
     assert lib.crl_rollout(prob(horizon=0), dummy, None, 0, dummy, None, None) == -1
@@ -71,7 +81,9 @@ def test_argument_validation_happens_before_any_cuda_call():
     assert lib.crl_forward_pass(prob(), ctypes.byref(bad_opts), dummy, dummy, dummy, dummy, dummy, dummy, dummy, dummy,
                                 None) == -1
     assert lib.crl_backward_dense(5, 2, 0, 1, 10, dummy, dummy, dummy, dummy, dummy, None) == -2
-    assert lib.crl_solve_workspace_bytes(ctypes.byref(prob(model=9)), ctypes.byref(opts)) == 0
+    assert lib.crl_backward_dense(4, 1, 1, 1, 10, dummy, dummy, dummy, dummy, dummy, None) == -2   # FP64 only
+    assert lib.crl_solve_workspace_bytes(ctypes.byref(prob(model=10)), ctypes.byref(opts)) == 0
+    assert lib.crl_solve_workspace_bytes(ctypes.byref(prob(model=8, batch=33, horizon=10)), ctypes.byref(opts)) == 2 * 10 * 32 * (12 + 8 + 2) * 8
 
 
 def test_no_cpu_fallback():

@@ -22,8 +22,15 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",   # B200 only; no PTX for other targets
     "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
     "-fmad=false",                                  # contraction off: FMAs are explicit in the source
-    "-shared", "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fPIC",
 ]
+OBJ_DIR = os.path.join(PKG_DIR, "_obj")             # one object per translation unit (git-ignored), relinked on change
+# headers each translation unit depends on (besides the C ABI header)
+UNIT_HEADERS = {
+    "ilqr_kernels.cu": ("ilqr_common.cuh", "ilqr_models.cuh", "ilqr_core.cuh", "ilqr_coop.cuh", "ilqr_generic_host.h"),
+    "ilqr_generic.cu": ("ilqr_common.cuh", "ilqr_models.cuh", "ilqr_core.cuh", "ilqr_generic.cuh", "ilqr_generated.cuh",
+                        "ilqr_generic_host.h"),
+}
 
 
 def find_nvcc():
@@ -38,19 +45,39 @@ def is_stale():
     return any(os.path.getmtime(p) > built for p in SOURCES + HEADERS if os.path.exists(p))
 
 
+def _unit_stale(src, obj):
+    if not os.path.exists(obj):
+        return True
+    built = os.path.getmtime(obj)
+    deps = [src, HEADERS[-1]] + [os.path.join(CSRC, h) for h in UNIT_HEADERS[os.path.basename(src)]]
+    return any(os.path.getmtime(p) > built for p in deps if os.path.exists(p))
+
+
 def build_native(force: bool = False, verbose: bool = False) -> str:
-    """Compile the CUDA library if missing or older than its sources; return its path."""
+    """Compile the CUDA library if missing or older than its sources; return its path.  Every translation unit is
+    compiled to its own object (only the changed ones are recompiled) and the objects are linked into the library."""
     if not force and not is_stale():
         return LIB_PATH
     nvcc = find_nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found and %s is missing or stale: the CUDA library cannot be built" % LIB_PATH)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(OBJ_DIR, os.path.splitext(os.path.basename(src))[0] + ".o")
+        objs.append(obj)
+        if not force and not _unit_stale(src, obj):
+            continue
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose:
+            sys.stderr.write(proc.stderr)
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr[-4000:]))
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH] + objs
     proc = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose:
-        sys.stderr.write(proc.stderr)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr[-4000:]))
+        raise RuntimeError("nvcc link failed:\n%s\n%s" % (" ".join(cmd), proc.stderr[-4000:]))
     return LIB_PATH
 
 

@@ -127,8 +127,12 @@ constexpr long long gen_tile_reals(int T) {
     return (long long)T * 32 * (2 * G::D + G::M * G::N + G::M);
 }
 
+#ifndef CRL_GEN_MINB
+#define CRL_GEN_MINB 4
+#endif
+// 4 resident CTAs per SM (128 registers per thread): 75,776 resident threads, so the benchmark batch of 65,536 is one wave
 template <class G>
-__global__ void __launch_bounds__(kGenBlock) gen_solve_kernel(GenProblemDev pb, GenOpts op, const double* x0,
+__global__ void __launch_bounds__(kGenBlock, CRL_GEN_MINB) gen_solve_kernel(GenProblemDev pb, GenOpts op, const double* x0,
                                                               const double* u0, long long u0_sb, const double* J_init,
                                                               double* X_out, double* J_out, int* iters_out,
                                                               uint8_t* conv_out, double* J_trace, int8_t* alpha_trace,

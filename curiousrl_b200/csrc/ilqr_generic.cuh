@@ -92,10 +92,18 @@ CRL_HD void gen_backward(XV X, GenParams prm, int T, KV K, SV k) {
     constexpr int N = G::N, M = G::M, D = G::D;
     double V[N][N], v[N];
     for (int i = 0; i < N; ++i) { v[i] = 0.0; for (int j = 0; j < N; ++j) V[i][j] = 0.0; }
+    double xnext[D];
+    {
+        const double* row = X.row(T - 1);
+        for (int i = 0; i < D; ++i) xnext[i] = X.ld(row, i);
+    }
     for (int t = T - 1; t >= 0; --t) {
         double xu[D], p[G::P], F[N * D], c[D], C[D * D], Kt[M * N], kt[M];
-        const double* row = X.row(t);
-        for (int i = 0; i < D; ++i) xu[i] = X.ld(row, i);
+        for (int i = 0; i < D; ++i) xu[i] = xnext[i];
+        if (t > 0) {                                       // the row of step t-1 is loaded while step t computes
+            const double* row = X.row(t - 1);
+            for (int i = 0; i < D; ++i) xnext[i] = X.ld(row, i);
+        }
         prm.load(t, p);
         gen_derivs<G>(xu, p, F, c, C);
         dense_riccati_step<N, M, double>(F, c, C, V, v, Kt, kt);
@@ -116,20 +124,31 @@ CRL_HD double gen_rollout_closed(XV X, KV K, SV k, double alpha, GenParams prm, 
         for (int i = 0; i < D; ++i) xu[i] = X.ld(r0, i);          // row 0 copied, its action overwritten below
     }
     double J = 0.0;
+    // old row, K and k of the next step are loaded while the current step computes (they do not depend on it)
+    double xo_n[D], K_n[M * N], k_n[M], Kc[M * N], kc[M];
+    auto fetch = [&](int t) {
+        const double* ro = X.row(t);
+        for (int i = 0; i < D; ++i) xo_n[i] = X.ld(ro, i);
+        const double* Kr = K.row(t);
+        for (int i = 0; i < M * N; ++i) K_n[i] = K.ld(Kr, i);
+        const double* kr = k.row(t);
+        for (int a = 0; a < M; ++a) k_n[a] = k.ld(kr, a);
+    };
+    if (T > 1) fetch(0);
     for (int t = 0; t < T; ++t) {
         const bool last = (t == T - 1);
         if (!last) {
-            const double* ro = X.row(t);
-            for (int i = 0; i < D; ++i) xo[i] = X.ld(ro, i);
-            const double* Kr = K.row(t);
-            const double* kr = k.row(t);
+            for (int i = 0; i < D; ++i) xo[i] = xo_n[i];
+            for (int i = 0; i < M * N; ++i) Kc[i] = K_n[i];
+            for (int a = 0; a < M; ++a) kc[a] = k_n[a];
+            if (t + 1 < T - 1) fetch(t + 1);
             double dx[N];
             for (int j = 0; j < N; ++j) dx[j] = xu[j] - xo[j];
             for (int a = 0; a < M; ++a) {
                 // delta_u = K dx + alpha k;  u = u_old + delta_u  (ilqr_dynamic_model.py:123-126)
-                double acc = K.ld(Kr, a * N + 0) * dx[0];
-                for (int j = 1; j < N; ++j) acc = fmadd(K.ld(Kr, a * N + j), dx[j], acc);
-                const double du = acc + alpha * k.ld(kr, a);
+                double acc = Kc[a * N + 0] * dx[0];
+                for (int j = 1; j < N; ++j) acc = fmadd(Kc[a * N + j], dx[j], acc);
+                const double du = acc + alpha * kc[a];
                 xu[N + a] = gen_clamp<G>(xo[N + a] + du, N + a);
             }
             G::step(xu, xn);

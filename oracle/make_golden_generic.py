@@ -36,6 +36,8 @@ CONFIGS = {
     "Generic_Vehicle_T150": ("VehicleTracking", dict(T=150), 6),
     "Generic_CarParking_T500": ("CarParking", dict(T=500), 4),
     "Generic_Vehicle_T40": ("VehicleTracking", dict(T=40), 6),          # short horizon, fast CPU checks
+    # the reference's default max_line_search = 50 (CarParking 17 iterations, J = 22258.98642621647)
+    "Generic_CarParking_T500_ls50": ("CarParking", dict(T=500), 3, 50),
 }
 MAX_ITER = 100
 
@@ -51,15 +53,16 @@ def same_scenario(ref, ours):
 
 
 def make(tag):
-    cls_name, kwargs, batch = CONFIGS[tag]
+    cls_name, kwargs, batch = CONFIGS[tag][:3]
+    max_ls = CONFIGS[tag][3] if len(CONFIGS[tag]) > 3 else mg.MAX_LINE_SEARCH
     t0 = time.time()
     scenario = getattr(ref_models, cls_name)(**kwargs)
     same_scenario(scenario, getattr(our_models, cls_name)(**kwargs))
-    algo = BasiciLQR(max_line_search=mg.MAX_LINE_SEARCH, max_iter=MAX_ITER)
+    algo = BasiciLQR(max_line_search=max_ls, max_iter=MAX_ITER)
     algo.init(scenario)
     x0_default = scenario.init_state[:, 0].copy()
     out = dict(model=np.str_(cls_name), T=np.int64(scenario.T), n=np.int64(scenario.n), m=np.int64(scenario.m),
-               max_line_search=np.int64(mg.MAX_LINE_SEARCH), max_iter=np.int64(MAX_ITER))
+               max_line_search=np.int64(max_ls), max_iter=np.int64(MAX_ITER))
     rec = mg.Recorder(algo)
     first = mg.run(algo, rec, x0_default)
     rec.stage_iters = {0, 1, first["iters"] - 1}

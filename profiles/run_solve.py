@@ -15,7 +15,7 @@ import torch  # noqa: E402
 from curiousrl_b200 import logger  # noqa: E402
 from curiousrl_b200.algorithm.ilqr_solver import BasiciLQR  # noqa: E402
 import curiousrl_b200.scenario.dynamic_model as models  # noqa: E402
-from curiousrl_b200.utils.synthetic import synthetic_batch  # noqa: E402
+from curiousrl_b200.utils.synthetic import ARM_GEOMETRY, synthetic_batch, synthetic_init_states  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--model", default="ThreeLinkPlanarManipulator")
@@ -33,9 +33,12 @@ kw = dict(max_line_search=10, dtype=a.dtype, verify=False, occupancy=a.occupancy
 if not a.converge:
     kw.update(is_check_stop=False, max_iter=a.iters)
 algo = BasiciLQR(**kw).init(getattr(models, a.model)(T=a.horizon))
-x0, tgt = synthetic_batch(a.model, a.batch, seed=1234)
+if a.model in ARM_GEOMETRY:
+    x0, tgt = synthetic_batch(a.model, a.batch, seed=1234)
+    tgt = algo._dev.real(tgt)
+else:                                  # generated-model scenarios: perturbed initial states, the scenario's own add_param
+    x0, tgt = synthetic_init_states(getattr(models, a.model)(T=a.horizon), a.batch, seed=1234), None
 x0 = algo._dev.real(x0)
-tgt = algo._dev.real(tgt)
 for _ in range(a.repeat):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()

@@ -33,7 +33,7 @@ def rel(a, b):
     return float(np.nanmax(np.abs(a - b)) / max(1e-300, np.nanmax(np.abs(b))))
 
 
-@pytest.mark.parametrize("tag", TAGS[2:])
+@pytest.mark.parametrize("tag", TAGS[2:] + ["Generic_CarParking_T500_ls50"])
 def test_oracle_is_bit_exact_on_the_reference_vectors(golden, tag):
     g = golden(tag)
     prob = _prob(g)
@@ -121,3 +121,17 @@ def test_device_math_end_to_end(golden, tag):
         r = hs.solve(g["batch_x0"][b], sc.add_param, int(g["T"]), **kw)
         assert r["iters"] == int(g["batch_iters"][b])
         assert abs(r["J"] - float(g["batch_J"][b])) <= max(1e-9, 4.0 * spread[b]) * abs(float(g["batch_J"][b]))
+
+
+def test_knife_edge_problem_terminates_no_worse_than_the_reference(golden):
+    """CarParking with the reference's default max_line_search = 50 (17 iterations,
+    J = 22258.98642621647): the reference itself takes 12 ... 33 iterations under 1e-15 noise on K, k, so the
+    iteration count cannot be demanded; the device math must terminate normally at a cost no worse than the
+    reference's worst outcome (SURVEY.md section 4.3 protocol)."""
+    g = golden("Generic_CarParking_T500_ls50")
+    assert int(g["default_iters"]) == 17 and float(g["default_J"]) == 22258.98642621647
+    assert len(set(g["default_noise_iters"].tolist())) > 1            # knife edge: the reference moves
+    sc = make_scenario("CarParking", 500)
+    r = GenericHostSim("CarParking").solve(g["default_x0"], sc.add_param, 500, max_iter=100, max_line_search=50)
+    worst = max(float(g["default_J"]), float(g["default_noise_J"].max()))
+    assert r["iters"] < 100 and np.isfinite(r["J"]) and r["J"] <= worst * (1.0 + 1e-6)

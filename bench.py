@@ -172,7 +172,8 @@ def _cpu_solve(job):
         if pb is None:
             iters += orc.solve(prob, x0[b], None if tgt is None else tgt[b], max_line_search=MAX_LINE_SEARCH)["iters"]
         else:
-            iters += int(orc.solve_log_barrier(pb, prob, x0[b], tgt[b], max_line_search=MAX_LINE_SEARCH)["inner_iters"].sum())
+            iters += int(orc.solve_log_barrier(pb, prob, x0[b], None if tgt is None else tgt[b],
+                                               max_line_search=MAX_LINE_SEARCH)["inner_iters"].sum())
     return iters, time.perf_counter() - t0
 
 

@@ -11,12 +11,13 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int
 
 from . import build as _build
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MODEL_IDS = {"TwoLinkPlanarManipulator": 0, "ThreeLinkPlanarManipulator": 1, "RoboticArmTracking": 2}
 # the same scenarios under LogBarrieriLQR's cost (include/curiousrl_b200.h: CRL_*_BARRIER); FP64 only
 BARRIER_MODEL_IDS = {name: mid + 3 for name, mid in MODEL_IDS.items()}
 # scenarios with a GENERATED device model (CRL_GEN_*; curiousrl_b200/codegen.py): FP64, bounds compiled in
 GENERIC_MODEL_IDS = {"CartPoleSwingUp1": 6, "CartPoleSwingUp2": 7, "VehicleTracking": 8, "CarParking": 9}
+GENERIC_BARRIER_MODEL_IDS = {name: mid + 4 for name, mid in GENERIC_MODEL_IDS.items()}      # CRL_GEN_*_BARRIER
 DTYPE_IDS = {"float64": 0, "float32": 1}
 LINE_SEARCH_IDS = {"vanilla": 0, "feasibility": 1, "none": 2}
 STOPPING_IDS = {"relative": 0, "vanilla": 1}

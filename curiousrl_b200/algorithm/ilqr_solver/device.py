@@ -45,8 +45,8 @@ class DeviceModel:
         if model_name not in _native.MODEL_IDS and not self.generic:
             raise Exception('Scenario "%s" has no device model in curiousrl_b200 (supported: %s); '
                             "there is no CPU fallback." % (model_name, ", ".join(list(_native.MODEL_IDS) + list(_native.GENERIC_MODEL_IDS))))
-        if self.generic and (barrier or dtype != "float64"):
-            raise ValueError('the generated device model of "%s" is compiled for float64 and the plain cost only' % model_name)
+        if self.generic and dtype != "float64":
+            raise ValueError('the generated device model of "%s" is compiled for float64 only' % model_name)
         if dtype not in _TORCH_DTYPE:
             raise ValueError("dtype must be 'float64' or 'float32'")
         self.lib = _native.load()
@@ -56,7 +56,7 @@ class DeviceModel:
         if barrier and dtype != "float64":
             raise ValueError("the log-barrier cost is compiled for float64 only")
         self.model_name = model_name
-        self.model_id = (_native.GENERIC_MODEL_IDS if self.generic else
+        self.model_id = ((_native.GENERIC_BARRIER_MODEL_IDS if barrier else _native.GENERIC_MODEL_IDS) if self.generic else
                          _native.BARRIER_MODEL_IDS if barrier else _native.MODEL_IDS)[model_name]
         self.n, self.m, self.p = _native.model_dims(self.model_id)
         self.d = self.n + self.m
@@ -240,11 +240,15 @@ class DeviceModel:
         x0 = self.real(x0).reshape(-1, self.n)
         B = x0.shape[0]
         stage_params = self.real(stage_params)
-        if stage_params.dim() != 3 or stage_params.shape[-1] != self.p or stage_params.shape[0] not in (1, B):
-            raise ValueError("stage_params must be [B, S, p] or [1, S, p]")
+        if stage_params.dim() not in (3, 4) or stage_params.shape[-1] != self.p or stage_params.shape[0] not in (1, B):
+            raise ValueError("stage_params must be [B, S, p] / [1, S, p], or [B, S, T, p] / [1, S, T, p] (generated models)")
+        if stage_params.dim() == 4 and (not self.generic or stage_params.shape[2] != self.T):
+            raise ValueError("time-varying stage rows [.., S, T, p] are for the generated models")
         S = int(stage_params.shape[1])
-        sb = 0 if (stage_params.shape[0] == 1 and B != 1) else S * self.p
-        prob = _native.Problem(self.model_id, self.dtype_id, B, self.T, 0, sb, stage_params.data_ptr(), self.u_lo, self.u_hi)
+        per_b = S * self.p * (self.T if stage_params.dim() == 4 else 1)
+        sb = 0 if (stage_params.shape[0] == 1 and B != 1) else per_b
+        st = self.p if stage_params.dim() == 4 else 0
+        prob = _native.Problem(self.model_id, self.dtype_id, B, self.T, st, sb, stage_params.data_ptr(), self.u_lo, self.u_hi)
         u0t, u0s = self._u0(u0, B)
         ws = self.workspace(prob, opts)
         if J_init is not None:

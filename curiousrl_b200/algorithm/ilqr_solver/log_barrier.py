@@ -42,6 +42,8 @@ class _RealCostOwner:
 
     def _params_for(self, B: int) -> torch.Tensor:
         dev = self._algo._real_dev
+        if self._algo._real_add_param is None:            # scenario without add_param: one unused zero column
+            return dev.real(np.zeros((dev.T, dev.p))).reshape(1, dev.T, dev.p)
         ap = np.asarray(self._algo._obj_fun._add_param, dtype=np.float64)[:, :dev.p]
         return dev.real(ap).reshape(1, dev.T, dev.p)
 
@@ -82,25 +84,37 @@ class LogBarrieriLQR(iLQRWrapper):
             raise Exception('Scenario "' + scenario.name + '" cannot learn with LogBarrieriLQR')
         constr = np.asarray(scenario.constr, dtype=np.float64)
         n = int(scenario.init_state.shape[0])
-        if not (np.all(constr[:n, 0] == -np.inf) and np.all(constr[:n, 1] == np.inf)):
-            raise Exception('Scenario "%s": finite state bounds are not supported by the device models' % scenario.name)
-        if scenario.name not in _native.MODEL_IDS:
-            raise Exception('Scenario "%s" has no device model in curiousrl_b200; there is no CPU fallback.' % scenario.name)
-        lo, hi = _native.model_default_bounds(_native.MODEL_IDS[scenario.name])
-        if not (np.all(constr[n:, 0] == lo) and np.all(constr[n:, 1] == hi)):
-            raise Exception('Scenario "%s": the barrier cost is compiled for the action box [%g, %g]' % (scenario.name, lo, hi))
         T = int(scenario.init_action.shape[0])
+        self._generic = scenario.name in _native.GENERIC_MODEL_IDS
+        if self._generic:
+            # generated device model: the barrier sits on every finite bound of the compiled-in box, states included
+            compiled = np.asarray(_native.model_bounds(_native.GENERIC_MODEL_IDS[scenario.name]), dtype=np.float64)
+            if compiled.shape != constr.shape or not np.array_equal(compiled, constr):
+                raise Exception('Scenario "%s": the barrier cost is generated for constr = %s' % (scenario.name, compiled.tolist()))
+            lo = hi = 0.0
+        else:
+            if not (np.all(constr[:n, 0] == -np.inf) and np.all(constr[:n, 1] == np.inf)):
+                raise Exception('Scenario "%s": finite state bounds are not supported by the device models' % scenario.name)
+            if scenario.name not in _native.MODEL_IDS:
+                raise Exception('Scenario "%s" has no device model in curiousrl_b200; there is no CPU fallback.' % scenario.name)
+            lo, hi = _native.model_default_bounds(_native.MODEL_IDS[scenario.name])
+            if not (np.all(constr[n:, 0] == lo) and np.all(constr[n:, 1] == hi)):
+                raise Exception('Scenario "%s": the barrier cost is compiled for the action box [%g, %g]' % (scenario.name, lo, hi))
         self._dev = DeviceModel(scenario.name, T, lo, hi, device=self._device, barrier=True)
         self._real_dev = DeviceModel(scenario.name, T, lo, hi, device=self._device)
         self._dynamic_model = iLQRDynamicModel(self._dev, scenario.init_state, scenario.init_action, self)
+        self._real_add_param = scenario.add_param          # None for a scenario without add_param
         if scenario.add_param is None:
-            raise Exception('Scenario "%s" has no add_param (target)' % scenario.name)
-        add_param = np.hstack([np.asarray(scenario.add_param, dtype=np.float64), self._t[0] * np.ones((T, 1))])   # :100-101
+            if not self._generic:
+                raise Exception('Scenario "%s" has no add_param (target)' % scenario.name)
+            add_param = self._t[0] * np.ones((T, 1), dtype=np.float64)                                            # :96-98
+        else:
+            add_param = np.hstack([np.asarray(scenario.add_param, dtype=np.float64), self._t[0] * np.ones((T, 1))])   # :100-101
         self._obj_fun = iLQRObjectiveFunction(self._dev, add_param, self)
         self._real_obj_fun = iLQRObjectiveFunction(self._real_dev, None, _RealCostOwner(self))
         self._t_stale = None
-        if self._verify:
-            self._verify_against(scenario)
+        if self._verify and not self._generic:         # generated models: the plain model is verified by BasiciLQR.init; the
+            self._verify_against(scenario)             # barrier terms come from the same generator (tests pin them)
         return self
 
     def _verify_against(self, scenario):
@@ -186,6 +200,8 @@ class LogBarrieriLQR(iLQRWrapper):
         dev, rdev = self._dev, self._real_dev
         x0 = dev.real(init_state).reshape(-1, dev.n)
         B = x0.shape[0]
+        if self._generic:
+            return self._solve_batch_generic(x0, add_param, init_action, return_trajectory, fused)
         if add_param is None:
             tgt = dev.real(np.asarray(self._obj_fun._add_param, dtype=np.float64)[0, :rdev.p]).reshape(1, rdev.p).expand(B, rdev.p)
         else:
@@ -226,6 +242,45 @@ class LogBarrieriLQR(iLQRWrapper):
                                     res.converged)
         out.inner_iterations = inner
         out.real_obj_fun_value = rdev.cost(res.trajectory, tgt.contiguous())
+        self.last_result = out
+        _publish_batch(self, out, inner_iterations=inner, real_obj_fun_value=out.real_obj_fun_value)
+        return out
+
+    def _solve_batch_generic(self, x0, add_param, init_action, return_trajectory, fused) -> LogBarrierBatchResult:
+        """Generated device models: the scenario's own (time-varying) add_param is shared by the batch; stage rows
+        [1, S, T, p] = (add_param columns, t_s, t_{s-1})."""
+        if add_param is not None:
+            raise ValueError("the generated-model scenarios take their cost parameters from the scenario (add_param=None)")
+        dev, rdev = self._dev, self._real_dev
+        B, S, T = x0.shape[0], len(self._t), dev.T
+        base = np.asarray(self._obj_fun._add_param, dtype=np.float64)[:, :dev.p - 2]          # without the t column
+        u0 = self._dynamic_model._init_action if init_action is None else init_action
+        if isinstance(u0, np.ndarray) and not u0.any():
+            u0 = None
+        opts = self._opts(self._max_iter, self._is_check_stop)
+        rows = np.empty((1, S, T, dev.p), dtype=np.float64)
+        for s, t in enumerate(self._t):
+            rows[0, s, :, :dev.p - 2] = base
+            rows[0, s, :, dev.p - 2] = t
+            rows[0, s, :, dev.p - 1] = self._t[max(s - 1, 0)]
+        if fused:
+            res, inner = dev.solve_stages(opts, x0, dev.real(rows), u0=u0, J_init=None, return_trajectory=True)
+        else:
+            J_init = torch.full((B,), float("inf"), dtype=torch.float64, device=dev.device)
+            inner = torch.zeros((B, S), dtype=torch.int32, device=dev.device)
+            res = None
+            for s in range(S):
+                res = dev.solve(opts, x0, dev.real(rows[:, s]), u0=u0, J_init=J_init, return_trajectory=True)
+                inner[:, s] = res.iterations
+                u0 = res.trajectory[:, :, dev.n:].contiguous()
+                if self._is_check_stop:
+                    J_init = torch.where(res.converged.bool(), torch.full_like(res.obj_fun_value, float("inf")), res.obj_fun_value)
+                else:
+                    J_init = res.obj_fun_value.clone()
+        out = LogBarrierBatchResult(res.trajectory if return_trajectory else None, res.obj_fun_value, inner.sum(dim=1).to(torch.int32),
+                                    res.converged)
+        out.inner_iterations = inner
+        out.real_obj_fun_value = rdev.cost(res.trajectory, _RealCostOwner(self)._params_for(B))
         self.last_result = out
         _publish_batch(self, out, inner_iterations=inner, real_obj_fun_value=out.real_obj_fun_value)
         return out

@@ -31,6 +31,8 @@ HEADER_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "
 
 #: scenario class name -> model id of the C ABI (include/curiousrl_b200.h: CRL_GEN_*)
 GENERIC_MODEL_IDS = {"CartPoleSwingUp1": 6, "CartPoleSwingUp2": 7, "VehicleTracking": 8, "CarParking": 9}
+#: the same scenarios under LogBarrieriLQR's cost (CRL_GEN_*_BARRIER)
+GENERIC_BARRIER_MODEL_IDS = {name: mid + 4 for name, mid in GENERIC_MODEL_IDS.items()}
 
 
 class _DevicePrinter(C99CodePrinter):
@@ -87,6 +89,7 @@ def generate_struct(scenario) -> str:
            "struct Gen%s {" % name,
            "    static constexpr int N = %d, M = %d, D = %d, P = %d;" % (n, m, d, p),
            "    static constexpr int kModelId = %d;" % GENERIC_MODEL_IDS[name],
+           "    static constexpr bool kBarrier = false;",
            "    CRL_GEN_FN double lo(int i) { constexpr double b[D] = {%s}; return b[i]; }" % ", ".join(_fmt_bound(v) for v in constr[:, 0]),
            "    CRL_GEN_FN double hi(int i) { constexpr double b[D] = {%s}; return b[i]; }" % ", ".join(_fmt_bound(v) for v in constr[:, 1]),
            "    CRL_GEN_FN void step(const double* x, double* xn) {"]
@@ -103,6 +106,43 @@ def generate_struct(scenario) -> str:
     return "\n".join(out)
 
 
+def generate_barrier_struct(scenario) -> str:
+    """`Gen<name>Barrier`: the scenario under LogBarrieriLQR's cost (log_barrier_ilqr.py:84-101) - every finite bound,
+    state bounds included, adds (-1/t) log(-(lo - x_u[i])) / (-1/t) log(-(x_u[i] - hi)).  Dynamics and box are the
+    plain model's; the parameter row is (the scenario's add_param columns, t, t0) with t0 = the stale barrier
+    parameter the first backward pass of an inner loop still sees (ilqr_generic.cuh)."""
+    printer = _DevicePrinter()
+    xu = list(scenario.x_u_var)
+    d = len(xu)
+    pv = [] if scenario.add_param_var is None else list(scenario.add_param_var)
+    t_var = sp.symbols("t")
+    constr = np.asarray(scenario.constr, dtype=np.float64)
+    l = scenario.obj_fun
+    for i, c in enumerate(constr):                       # same construction order as the reference (:91-95)
+        if not np.isinf(c[0]):
+            l = l + (-1 / t_var) * sp.log(-(c[0] - xu[i]))
+        if not np.isinf(c[1]):
+            l = l + (-1 / t_var) * sp.log(-(xu[i] - c[1]))
+    g = sp.derive_by_array(l, xu)
+    H = np.asarray(sp.derive_by_array(g, xu)) + 1e-100 * np.eye(d)
+    name = type(scenario).__name__
+    ax, ap = _aliases(xu, "x"), _aliases(pv + [t_var], "p")
+    out = ["// %s under the log-barrier cost  (parameter row: %d scenario columns, t, t0)" % (name, len(pv)),
+           "struct Gen%sBarrier : Gen%s {" % (name, name),
+           "    static constexpr int P = %d;" % (len(pv) + 2),
+           "    static constexpr int kT = %d;                   // index of t in the parameter row; t0 follows" % len(pv),
+           "    static constexpr int kModelId = %d;" % GENERIC_BARRIER_MODEL_IDS[name],
+           "    static constexpr bool kBarrier = true;",
+           "    CRL_GEN_FN double cost(const double* x, const double* p) {"]
+    out += ax + ap + ["        return %s;" % printer.doprint(sp.sympify(l))]
+    out += ["    }", "    CRL_GEN_FN void grad(const double* x, const double* p, double* c) {"]
+    out += ax + ap + _emit_assignments(printer, "c", list(g))
+    out += ["    }", "    CRL_GEN_FN void hess(const double* x, const double* p, double* C) {"]
+    out += ax + ap + _emit_assignments(printer, "C", [H[i, j] for i in range(d) for j in range(d)])
+    out += ["    }", "};", ""]
+    return "\n".join(out)
+
+
 def generate_header(scenarios) -> str:
     head = ['// GENERATED by curiousrl_b200/codegen.py from scenario/dynamic_model/vehicles.py - do not edit.',
             '// sympy %s.  Device models of the scenarios without a hand-written model (SURVEY.md 8(f) N2);' % sp.__version__,
@@ -111,7 +151,7 @@ def generate_header(scenarios) -> str:
             '#if defined(__CUDACC__)', '#define CRL_GEN_FN __host__ __device__ __forceinline__ static',
             '#else', '#define CRL_GEN_FN inline static', '#endif',
             '#define CRL_GEN_INF (__builtin_huge_val())', '', 'namespace crl {', '']
-    body = [generate_struct(s) for s in scenarios]
+    body = [generate_struct(s) for s in scenarios] + [generate_barrier_struct(s) for s in scenarios]
     return "\n".join(head + body + ["}  // namespace crl", ""])
 
 

@@ -136,7 +136,8 @@ __global__ void __launch_bounds__(kGenBlock, CRL_GEN_MINB) gen_solve_kernel(GenP
                                                               const double* u0, long long u0_sb, const double* J_init,
                                                               double* X_out, double* J_out, int* iters_out,
                                                               uint8_t* conv_out, double* J_trace, int8_t* alpha_trace,
-                                                              double* ws) {
+                                                              double* ws, int n_stage, long long stage_stride,
+                                                              int* stage_iters) {
     constexpr int D = G::D, M = G::M, N = G::N;
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -152,7 +153,8 @@ __global__ void __launch_bounds__(kGenBlock, CRL_GEN_MINB) gen_solve_kernel(GenP
         gen_solve_one<G>(x0 + b * N, u0 ? u0 + b * u0_sb : nullptr, M, pb.prm(b), T, op,
                          J_init ? J_init[b] : (double)INFINITY, Xa, Xb, Kv, kv, &J, &iters, &conv, &in_a,
                          J_trace ? J_trace + b * op.max_iter : nullptr,
-                         alpha_trace ? (signed char*)alpha_trace + b * op.max_iter : nullptr);
+                         alpha_trace ? (signed char*)alpha_trace + b * op.max_iter : nullptr, n_stage, stage_stride,
+                         stage_iters ? stage_iters + b * n_stage : nullptr);
         J_out[b] = J;
         iters_out[b] = iters;
         conv_out[b] = (uint8_t)conv;
@@ -180,10 +182,15 @@ __global__ void __launch_bounds__(kGenBlock, CRL_GEN_MINB) gen_solve_kernel(GenP
         case CRL_GEN_CART_POLE_2: { using G = GenCartPoleSwingUp2; __VA_ARGS__; } break;       \
         case CRL_GEN_VEHICLE_TRACKING: { using G = GenVehicleTracking; __VA_ARGS__; } break;   \
         case CRL_GEN_CAR_PARKING: { using G = GenCarParking; __VA_ARGS__; } break;             \
+        case CRL_GEN_CART_POLE_1_BARRIER: { using G = GenCartPoleSwingUp1Barrier; __VA_ARGS__; } break;      \
+        case CRL_GEN_CART_POLE_2_BARRIER: { using G = GenCartPoleSwingUp2Barrier; __VA_ARGS__; } break;      \
+        case CRL_GEN_VEHICLE_TRACKING_BARRIER: { using G = GenVehicleTrackingBarrier; __VA_ARGS__; } break;  \
+        case CRL_GEN_CAR_PARKING_BARRIER: { using G = GenCarParkingBarrier; __VA_ARGS__; } break;            \
         default: break;                                                                        \
     }
 
-bool gen_is_model(int model) { return model >= CRL_GEN_CART_POLE_1 && model <= CRL_GEN_CAR_PARKING; }
+bool gen_is_model(int model) { return model >= CRL_GEN_CART_POLE_1 && model <= CRL_GEN_CAR_PARKING_BARRIER; }
+bool gen_is_barrier(int model) { return model >= CRL_GEN_CART_POLE_1_BARRIER && model <= CRL_GEN_CAR_PARKING_BARRIER; }
 
 int gen_dims(int model, int* n, int* m, int* p) {
     if (!gen_is_model(model)) return -1;
@@ -236,12 +243,15 @@ size_t gen_solve_workspace_bytes(const crl_problem_t* prob) {
 
 int gen_launch_solve(const crl_problem_t* prob, const crl_solver_opts_t* opts, const double* x0, const double* u0,
                      long long u0_sb, const double* J_init, double* X, double* J, int32_t* iters, uint8_t* converged,
-                     double* J_trace, int8_t* alpha_trace, void* workspace, cudaStream_t s) {
+                     double* J_trace, int8_t* alpha_trace, void* workspace, cudaStream_t s, int n_stage,
+                     int32_t* stage_iters) {
     // whole warps: the result write-out is a warp-cooperative loop
     const unsigned grid = blocks(((prob->batch + 31) / 32) * 32);
     CRL_GEN_DISPATCH(prob->model, (gen_solve_kernel<G><<<grid, kGenBlock, 0, s>>>(
                                       to_gen(prob), to_gen(opts), x0, u0, u0_sb, J_init, X, J, iters, converged, J_trace,
-                                      alpha_trace, (double*)workspace)));
+                                      alpha_trace, (double*)workspace, n_stage,
+                                      prob->params_stride_t ? (long long)prob->horizon * G::P : (long long)G::P,
+                                      stage_iters)));
     return (int)cudaGetLastError();
 }
 

@@ -87,8 +87,11 @@ CRL_HD void gen_derivs(const double* xu, const double* p, double* F, double* c, 
 }
 
 // Backward pass: K [T][M*N], k [T][M] from X.
+// `first`: the first backward pass of an inner loop of LogBarrieriLQR still sees cost derivatives taken with the
+// previous barrier parameter (the reference evaluates C, c in the forward pass, before its outer loop moves t on,
+// log_barrier_ilqr.py:121-133): barrier models take t from the stale entry p[kT + 1] then.
 template <class G, class XV, class KV, class SV>
-CRL_HD void gen_backward(XV X, GenParams prm, int T, KV K, SV k) {
+CRL_HD void gen_backward(XV X, GenParams prm, int T, KV K, SV k, bool first = false) {
     constexpr int N = G::N, M = G::M, D = G::D;
     double V[N][N], v[N];
     for (int i = 0; i < N; ++i) { v[i] = 0.0; for (int j = 0; j < N; ++j) V[i][j] = 0.0; }
@@ -105,6 +108,9 @@ CRL_HD void gen_backward(XV X, GenParams prm, int T, KV K, SV k) {
             for (int i = 0; i < D; ++i) xnext[i] = X.ld(row, i);
         }
         prm.load(t, p);
+        if constexpr (G::kBarrier) {
+            if (first) p[G::kT] = p[G::kT + 1];
+        }
         gen_derivs<G>(xu, p, F, c, C);
         dense_riccati_step<N, M, double>(F, c, C, V, v, Kt, kt);
         double* Kr = K.row(t);
@@ -172,41 +178,53 @@ struct GenOpts {
 };
 
 // The whole solve of one trajectory.  Xa / Xb: two trajectory buffers (the result ends in *final_in_a ? Xa : Xb).
+// n_stage > 1 (barrier models): LogBarrieriLQR's outer loop (log_barrier_ilqr.py:121-146) - one inner loop per
+// parameter set `prm.ptr + s * stage_stride`, the trajectory is kept, the iteration counter restarts and the stored
+// cost is reset to +inf after a loop that ended by the stopping criterion; stage_iters[s] = iterations of loop s.
 template <class G, class XV, class KV, class SV>
 CRL_HD void gen_solve_one(const double* x0, const double* U, int su_t, GenParams prm, int T, const GenOpts& op,
                           double J_init, XV Xa, XV Xb, KV K, SV k, double* J_out, int* iters_out, int* conv_out,
-                          bool* final_in_a, double* J_trace, signed char* alpha_trace) {
+                          bool* final_in_a, double* J_trace, signed char* alpha_trace, int n_stage = 1,
+                          long long stage_stride = 0, int* stage_iters = nullptr) {
     gen_rollout_open<G>(x0, U, su_t, prm, T, Xa);
     bool in_a = true;
     double J_last = J_init;
     const int tries = op.ls_method == 2 /* CRL_LS_NONE */ ? 1 : op.max_ls;
-    int it = 0;
+    int total = 0;
     bool stopped = false;
-    while (it < op.max_iter) {
-        XV Xc = in_a ? Xa : Xb, Xn = in_a ? Xb : Xa;
-        gen_backward<G>(Xc, prm, T, K, k);
-        bool accepted = false;
-        double J_new = J_last, alpha = 1.0;
-        int taken = -1;
-        for (int a = 0; a < tries && !accepted; ++a) {
-            const double Jt = gen_rollout_closed<G>(Xc, K, k, alpha, prm, T, Xn);
-            if (op.ls_method == 2 || ls_accept(Jt, J_last, op.ls_method == 1)) {
-                accepted = true;
-                J_new = Jt;
-                taken = a;
+    for (int s = 0; s < n_stage; ++s) {
+        const GenParams ps{prm.ptr + (size_t)s * stage_stride, prm.stride_t};
+        if (s > 0 && stopped) J_last = (double)INFINITY;                       // log_barrier_ilqr.py:141
+        int it = 0;
+        stopped = false;
+        while (it < op.max_iter) {
+            XV Xc = in_a ? Xa : Xb, Xn = in_a ? Xb : Xa;
+            gen_backward<G>(Xc, ps, T, K, k, it == 0);
+            bool accepted = false;
+            double J_new = J_last, alpha = 1.0;
+            int taken = -1;
+            for (int a = 0; a < tries && !accepted; ++a) {
+                const double Jt = gen_rollout_closed<G>(Xc, K, k, alpha, ps, T, Xn);
+                if (op.ls_method == 2 || ls_accept(Jt, J_last, op.ls_method == 1)) {
+                    accepted = true;
+                    J_new = Jt;
+                    taken = a;
+                }
+                alpha = alpha * op.gamma;
             }
-            alpha = alpha * op.gamma;
+            const bool stop = stop_test(J_new, J_last, op.criterion, op.stop_method == 0);
+            J_last = J_new;
+            if (accepted) in_a = !in_a;
+            if (J_trace) J_trace[it] = J_new;
+            if (alpha_trace) alpha_trace[it] = (signed char)taken;
+            ++it;
+            if (stop && op.check_stop) { stopped = true; break; }
         }
-        const bool stop = stop_test(J_new, J_last, op.criterion, op.stop_method == 0);
-        J_last = J_new;
-        if (accepted) in_a = !in_a;
-        if (J_trace) J_trace[it] = J_new;
-        if (alpha_trace) alpha_trace[it] = (signed char)taken;
-        ++it;
-        if (stop && op.check_stop) { stopped = true; break; }
+        if (stage_iters) stage_iters[s] = it;
+        total += it;
     }
     *J_out = J_last;
-    *iters_out = it;
+    *iters_out = total;
     *conv_out = stopped ? 1 : 0;
     *final_in_a = in_a;
 }

@@ -12,6 +12,7 @@
 namespace crl {
 
 bool gen_is_model(int model);                                    // CRL_GEN_* ids
+bool gen_is_barrier(int model);                                  // CRL_GEN_*_BARRIER ids
 int gen_dims(int model, int* n, int* m, int* p);                 // 0 = ok
 int gen_bounds(int model, double* lo, double* hi);               // d entries each
 
@@ -28,6 +29,7 @@ int gen_launch_forward(const crl_problem_t* prob, const crl_solver_opts_t* opts,
 size_t gen_solve_workspace_bytes(const crl_problem_t* prob);
 int gen_launch_solve(const crl_problem_t* prob, const crl_solver_opts_t* opts, const double* x0, const double* u0,
                      long long u0_sb, const double* J_init, double* X, double* J, int32_t* iters, uint8_t* converged,
-                     double* J_trace, int8_t* alpha_trace, void* workspace, cudaStream_t s);
+                     double* J_trace, int8_t* alpha_trace, void* workspace, cudaStream_t s, int n_stage,
+                     int32_t* stage_iters);
 
 }  // namespace crl

@@ -1718,10 +1718,10 @@ static int solve_impl(const crl_problem_t* prob, const crl_solver_opts_t* opts, 
     if (n_stage > 1) {
         // one parameter row per stage, constant over the horizon; barrier models only; no per-iteration traces
         const bool barrier = prob->model == CRL_TWO_LINK_BARRIER || prob->model == CRL_THREE_LINK_BARRIER ||
-                             prob->model == CRL_ROBOTIC_ARM_BARRIER;
+                             prob->model == CRL_ROBOTIC_ARM_BARRIER || gen_is_barrier(prob->model);
         if (!barrier) return CRL_ERR_UNSUPPORTED_MODEL;
-        if (n_stage >= 128 || opts->max_iter > kStageItMask || prob->params_stride_t != 0 || J_trace || alpha_trace)
-            return CRL_ERR_BAD_ARGUMENT;
+        if (n_stage >= 128 || opts->max_iter > kStageItMask || J_trace || alpha_trace) return CRL_ERR_BAD_ARGUMENT;
+        if (prob->params_stride_t != 0 && !gen_is_barrier(prob->model)) return CRL_ERR_BAD_ARGUMENT;
         if (prob->batch > 0 && !stage_iters) return CRL_ERR_BAD_ARGUMENT;
     }
     if (prob->batch == 0) return CRL_OK;
@@ -1736,7 +1736,8 @@ static int solve_impl(const crl_problem_t* prob, const crl_solver_opts_t* opts, 
     cudaStream_t s = (cudaStream_t)stream;
     if (gen_is_model(prob->model))
         return cuda_status((cudaError_t)gen_launch_solve(prob, opts, (const double*)x0, (const double*)u0, u0_stride_b, J_init,
-                                                         (double*)X, J, iters, converged, J_trace, alpha_trace, workspace, s));
+                                                         (double*)X, J, iters, converged, J_trace, alpha_trace, workspace, s,
+                                                         n_stage, stage_iters));
     size_t qbytes = 0;
     int grid = 0, warps = 0;
     long long slot_elems = 0;

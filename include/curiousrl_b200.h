@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CRL_ABI_VERSION 5
+#define CRL_ABI_VERSION 6
 
 typedef void* crl_stream_t; /* cudaStream_t */
 
@@ -49,7 +49,14 @@ enum crl_model {              /* scenario.name -> precompiled device model      
     CRL_GEN_CART_POLE_1 = 6,       /* CartPoleSwingUp1  cart_pole_swingup1.py:16   n=4 m=1 p=5 */
     CRL_GEN_CART_POLE_2 = 7,       /* CartPoleSwingUp2  cart_pole_swingup2.py:16   n=5 m=1 p=6 */
     CRL_GEN_VEHICLE_TRACKING = 8,  /* VehicleTracking   vehicle_tracking.py:15     n=4 m=2 p=1 (one unused zero column) */
-    CRL_GEN_CAR_PARKING = 9        /* CarParking        car_parking.py:23          n=4 m=2 p=2 */
+    CRL_GEN_CAR_PARKING = 9,       /* CarParking        car_parking.py:23          n=4 m=2 p=2 */
+    /* ... under LogBarrieriLQR's cost: here the barrier also sits on the finite STATE bounds (log_barrier_ilqr.py:91-95
+       runs over every row of constr).  Parameter row = (the scenario's add_param columns, t, t0): p + 2 entries
+       (VehicleTracking, which has no add_param: (t, t0)).                                                            */
+    CRL_GEN_CART_POLE_1_BARRIER = 10,
+    CRL_GEN_CART_POLE_2_BARRIER = 11,
+    CRL_GEN_VEHICLE_TRACKING_BARRIER = 12,
+    CRL_GEN_CAR_PARKING_BARRIER = 13
 };
 enum crl_dtype { CRL_F64 = 0, CRL_F32 = 1 };
 enum crl_line_search { CRL_LS_VANILLA = 0, CRL_LS_FEASIBILITY = 1, CRL_LS_NONE = 2 }; /* ilqr_wrapper.py:74-146 */
@@ -163,6 +170,8 @@ int crl_solve(const crl_problem_t* prob, const crl_solver_opts_t* opts, const vo
  * the stored cost to +inf if the loop ended by the stopping criterion (:140-141).  Barrier models only
  * (CRL_*_BARRIER): row s is (target_x, target_y, t_s, t_{s-1}), t_{-1} = t_0 (the stale value the first
  * backward pass of a loop still sees).  n_stages = 1 is crl_solve without traces.
+ * Generated barrier models (CRL_GEN_*_BARRIER) may also carry time-varying rows: params [B][n_stages][T][p] with
+ * params_stride_t = p (stage stride T * p, params_stride_b = n_stages * T * p or 0 = shared).
  *  out: as crl_solve (iters = total over the stages; J, converged = the last stage's) +
  *       stage_iters [B][n_stages] iterations of every inner loop.
  *  workspace: crl_solve_workspace_bytes() of the same prob / opts.                                    */

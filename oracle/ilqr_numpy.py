@@ -301,9 +301,16 @@ class BarrierScenario:
         self.constr = scenario.constr
         self.dynamic_function = scenario.dynamic_function
         self.obj_fun = obj
-        self.add_param_var = (*scenario.add_param_var, t_var)
         T = int(scenario.init_action.shape[0])
-        self.add_param = np.hstack([np.asarray(scenario.add_param, dtype=np.float64), t0 * np.ones((T, 1))])
+        if scenario.add_param_var is None:                       # log_barrier_ilqr.py:86-88
+            self.add_param_var = (t_var,)
+        else:
+            self.add_param_var = (*scenario.add_param_var, t_var)
+        if scenario.add_param is None:                           # :96-98
+            self.add_param = t0 * np.ones((T, 1))
+        else:
+            self.add_param = np.hstack([np.asarray(scenario.add_param, dtype=np.float64), t0 * np.ones((T, 1))])
+        self.has_params = scenario.add_param is not None
 
 
 def solve_log_barrier(prob_barrier: Problem, prob_real: Problem, x0=None, target=None, t_list=(0.5, 1., 2., 5., 10., 20., 50., 100.),
@@ -315,7 +322,10 @@ def solve_log_barrier(prob_barrier: Problem, prob_real: Problem, x0=None, target
     still sees derivatives taken with the previous t."""
     T = prob_barrier.T
     P_real = prob_real.params(target)
-    P = np.hstack([P_real, t_list[0] * np.ones((T, 1))])
+    if prob_barrier.add_param.shape[1] == 1:                     # scenario without add_param: the row is (t) alone
+        P = t_list[0] * np.ones((T, 1))
+    else:
+        P = np.hstack([P_real, t_list[0] * np.ones((T, 1))])
     X = rollout(prob_barrier, x0, None)
     Fm, c, C = derivs(prob_barrier, X, P)
     J_last = np.inf

@@ -12,6 +12,7 @@ SRC = os.path.join(HERE, "hostsim_generic.cpp")
 DEPS = [SRC] + [os.path.join(ROOT, "curiousrl_b200", "csrc", f)
                 for f in ("ilqr_common.cuh", "ilqr_models.cuh", "ilqr_core.cuh", "ilqr_generic.cuh", "ilqr_generated.cuh")]
 MODEL_ID = {"CartPoleSwingUp1": 6, "CartPoleSwingUp2": 7, "VehicleTracking": 8, "CarParking": 9}
+BARRIER_ID = {name: mid + 4 for name, mid in MODEL_ID.items()}
 
 _lib = None
 
@@ -35,8 +36,8 @@ def _f64(a):
 
 
 class GenericHostSim:
-    def __init__(self, model):
-        self.mid = MODEL_ID[model]
+    def __init__(self, model, barrier=False):
+        self.mid = (BARRIER_ID if barrier else MODEL_ID)[model]
         n, m, p = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         assert lib().hg_dims(self.mid, ctypes.byref(n), ctypes.byref(m), ctypes.byref(p)) == 0
         self.n, self.m, self.p = n.value, m.value, p.value
@@ -85,15 +86,32 @@ class GenericHostSim:
         return Xn, J.value
 
     def solve(self, x0, P, T, max_iter=1000, is_check_stop=True, stopping_criterion=1e-6, max_line_search=10, gamma=0.5,
-              line_search_method=0, stopping_method=0, J_init=np.inf, u0=None):
+              line_search_method=0, stopping_method=0, J_init=np.inf, u0=None, stages=None):
+        """stages = None: one solve with parameter rows P.  stages = [S, T, p] (or [S, p]): LogBarrieriLQR's outer loop,
+        one inner loop per parameter set; the result carries `inner_iters`."""
         x0 = _f64(x0).reshape(-1)
         u0 = None if u0 is None else _f64(u0).reshape(T, self.m)
-        P, st = self._params(P, T)
+        n_stage, stage_stride, sit = 1, 0, None
+        if stages is not None:
+            stages = _f64(stages)
+            n_stage = stages.shape[0]
+            P, st = (stages, stages.shape[2]) if stages.ndim == 3 else (stages, 0)
+            stage_stride = T * stages.shape[2] if stages.ndim == 3 else stages.shape[1]
+            sit = np.zeros(n_stage, dtype=np.int32)
+        else:
+            P, st = self._params(P, T)
         X, J, iters, conv = np.zeros((T, self.d)), ctypes.c_double(), ctypes.c_int(), ctypes.c_int()
+        trace = stages is None
         Jt, at = np.full(max_iter, np.nan), np.full(max_iter, -2, dtype=np.int8)
         assert lib().hg_solve(self.mid, _p(x0), _p(u0), _p(P), st, T, max_iter, int(is_check_stop),
                               ctypes.c_double(stopping_criterion), max_line_search, ctypes.c_double(gamma),
                               line_search_method, stopping_method, ctypes.c_double(J_init), _p(X), ctypes.byref(J),
-                              ctypes.byref(iters), ctypes.byref(conv), _p(Jt), _p(at)) == 0
+                              ctypes.byref(iters), ctypes.byref(conv), _p(Jt) if trace else None, _p(at) if trace else None,
+                              n_stage, ctypes.c_longlong(stage_stride), _p(sit)) == 0
         n = iters.value
-        return dict(X=X, J=J.value, iters=n, converged=bool(conv.value), Js=Jt[:n], alphas=at[:n].astype(np.int32))
+        out = dict(X=X, J=J.value, iters=n, converged=bool(conv.value))
+        if trace:
+            out.update(Js=Jt[:n], alphas=at[:n].astype(np.int32))
+        else:
+            out["inner_iters"] = sit
+        return out

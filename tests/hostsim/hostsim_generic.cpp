@@ -15,6 +15,10 @@ using namespace crl;
         case 7: { using G = GenCartPoleSwingUp2; __VA_ARGS__; } break;              \
         case 8: { using G = GenVehicleTracking; __VA_ARGS__; } break;               \
         case 9: { using G = GenCarParking; __VA_ARGS__; } break;                    \
+        case 10: { using G = GenCartPoleSwingUp1Barrier; __VA_ARGS__; } break;      \
+        case 11: { using G = GenCartPoleSwingUp2Barrier; __VA_ARGS__; } break;      \
+        case 12: { using G = GenVehicleTrackingBarrier; __VA_ARGS__; } break;       \
+        case 13: { using G = GenCarParkingBarrier; __VA_ARGS__; } break;            \
         default: return -2;                                                         \
     }
 
@@ -59,14 +63,15 @@ extern "C" int hg_update(int model, const double* X, const double* K, const doub
 extern "C" int hg_solve(int model, const double* x0, const double* u0, const double* params, int stride_t, int T,
                         int max_iter, int check_stop, double criterion, int max_ls, double gamma, int ls_method,
                         int stop_method, double J_init, double* X_out, double* J_out, int* iters_out, int* conv_out,
-                        double* J_trace, signed char* alpha_trace) {
+                        double* J_trace, signed char* alpha_trace, int n_stage, long long stage_stride, int* stage_iters) {
     HG_DISPATCH(model, {
         std::vector<double> xa((size_t)T * G::D), xb((size_t)T * G::D), Kb((size_t)T * G::M * G::N), kb((size_t)T * G::M);
         GenOpts op{max_iter, check_stop, max_ls, ls_method, stop_method, criterion, gamma};
         bool in_a = true;
         gen_solve_one<G>(x0, u0, G::M, GenParams{params, stride_t}, T, op, J_init, View<double, G::D, 1>{xa.data()},
                          View<double, G::D, 1>{xb.data()}, View<double, G::M * G::N, 1>{Kb.data()},
-                         View<double, G::M, 1>{kb.data()}, J_out, iters_out, conv_out, &in_a, J_trace, alpha_trace);
+                         View<double, G::M, 1>{kb.data()}, J_out, iters_out, conv_out, &in_a, J_trace, alpha_trace, n_stage,
+                         stage_stride, stage_iters);
         const std::vector<double>& fin = in_a ? xa : xb;
         for (size_t i = 0; i < fin.size(); ++i) X_out[i] = fin[i];
     });

@@ -135,3 +135,51 @@ def test_knife_edge_problem_terminates_no_worse_than_the_reference(golden):
     r = GenericHostSim("CarParking").solve(g["default_x0"], sc.add_param, 500, max_iter=100, max_line_search=50)
     worst = max(float(g["default_J"]), float(g["default_noise_J"].max()))
     assert r["iters"] < 100 and np.isfinite(r["J"]) and r["J"] <= worst * (1.0 + 1e-6)
+
+
+# ----------------------------------------------------------------------------- LogBarrieriLQR on the generated models
+BARRIER_TAGS = ["LogBarrierGeneric_Vehicle_T150", "LogBarrierGeneric_CartPole1_T150", "LogBarrierGeneric_CartPole2_T150",
+                "LogBarrierGeneric_CarParking_T500"]
+
+
+def _stage_rows(sc, t_list, T):
+    base = np.zeros((T, 0)) if sc.add_param is None else np.asarray(sc.add_param, dtype=np.float64)
+    return np.stack([np.hstack([base, t_list[s] * np.ones((T, 1)), t_list[max(s - 1, 0)] * np.ones((T, 1))])
+                     for s in range(len(t_list))])
+
+
+@pytest.mark.parametrize("tag", BARRIER_TAGS[:2])
+def test_barrier_oracle_is_bit_exact(golden, tag):
+    """oracle.solve_log_barrier on the scenarios with state bounds / without add_param against the unmodified reference."""
+    g = golden(tag)
+    sc = make_scenario(str(g["model"]), int(g["T"]))
+    pb, pr = orc.Problem(orc.BarrierScenario(sc, float(g["t_list"][0])), use_numba=True), _prob(dict(model=g["model"], T=g["T"]))
+    X0 = orc.rollout(pb)
+    assert np.array_equal(X0, g["init_X"]) and orc.cost(pb, X0, pb.params()) == float(g["init_J"])
+    r = orc.solve_log_barrier(pb, pr, None, None, t_list=tuple(g["t_list"]), max_iter=int(g["max_iter"]),
+                              max_line_search=int(g["max_line_search"]))
+    assert r["inner_iters"].tolist() == g["def_inner_iters"].tolist()
+    assert np.array_equal(r["Js"], g["def_J"]) and np.array_equal(r["Jreals"], g["def_Jreal"])
+    assert np.array_equal(r["X"], g["def_X"])
+
+
+@pytest.mark.parametrize("tag", BARRIER_TAGS)
+def test_barrier_device_math(golden, tag):
+    """Generated barrier models on the host build: cost / gradient / Hessian of the barrier cost at the initial trajectory
+    (state bounds included), then the whole schedule of barrier parameters as ONE staged solve (the form the kernel
+    runs): the reference's iteration count in every inner loop and its final trajectory."""
+    g = golden(tag)
+    T = int(g["T"])
+    sc = make_scenario(str(g["model"]), T)
+    hs = GenericHostSim(str(g["model"]), barrier=True)
+    stages = _stage_rows(sc, g["t_list"], T)
+    assert hs.p == stages.shape[2]
+    x0 = np.asarray(sc.init_state, dtype=np.float64).reshape(-1)
+    X0, J0 = hs.rollout(x0, stages[0], T)
+    assert rel(X0, g["init_X"]) <= 1e-13 and abs(J0 - float(g["init_J"])) <= 1e-13 * abs(float(g["init_J"]))
+    _F, c, C = hs.derivs(X0, stages[0])
+    assert rel(c, g["init_c"]) <= 1e-13 and rel(C, g["init_C"]) <= 1e-13
+    r = hs.solve(x0, None, T, max_iter=int(g["max_iter"]), max_line_search=int(g["max_line_search"]),
+                 line_search_method=1, stages=stages)
+    assert r["inner_iters"].tolist() == g["def_inner_iters"].tolist()
+    assert rel(r["X"], g["def_X"]) <= 1e-8

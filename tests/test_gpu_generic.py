@@ -129,7 +129,69 @@ def test_unconstrained_variant_and_other_solvers_raise():
     from curiousrl_b200.algorithm.ilqr_solver import BasiciLQR, LogBarrieriLQR
     with pytest.raises(Exception, match="generated for constr"):
         BasiciLQR().init(models.VehicleTracking(is_with_constraints=False, T=20))
-    with pytest.raises(Exception):
-        LogBarrieriLQR().init(models.VehicleTracking(T=20))
+    with pytest.raises(Exception, match="generated for constr"):
+        LogBarrieriLQR().init(models.VehicleTracking(is_with_constraints=False, T=20))
     with pytest.raises(Exception):
         BasiciLQR(dtype="float32").init(models.VehicleTracking(T=20))
+
+
+# ----------------------------------------------------------------------------- LogBarrieriLQR on the generated models
+BARRIER_TAGS = ["LogBarrierGeneric_Vehicle_T150", "LogBarrierGeneric_CartPole1_T150", "LogBarrierGeneric_CartPole2_T150",
+                "LogBarrierGeneric_CarParking_T500"]
+
+
+def make_barrier_algo(g, **kw):
+    from curiousrl_b200 import logger
+    from curiousrl_b200.algorithm.ilqr_solver import LogBarrieriLQR
+    logger.set_level(45)
+    return LogBarrieriLQR(max_line_search=int(g["max_line_search"]), max_iter=int(g["max_iter"]), **kw).init(
+        make_scenario(str(g["model"]), int(g["T"])))
+
+
+@pytest.mark.parametrize("tag", BARRIER_TAGS)
+def test_barrier_cost_and_default_problem(golden, tag):
+    """Fixtures from the unmodified reference's LogBarrieriLQR(max_line_search=10, max_iter=100) (barrier terms on the
+    finite state bounds too).  Barrier cost, gradient and Hessian at the initial trajectory <= 1e-13; solve(): the
+    reference's iteration count in EVERY inner loop, real cost <= 1e-9, trajectory <= 1e-8."""
+    g = golden(tag)
+    algo = make_barrier_algo(g)
+    X0 = algo.dynamic_model.eval_traj()
+    assert rel(X0[:, :, 0], g["init_X"]) <= 1e-13
+    assert algo.obj_fun.eval_obj_fun(X0) == pytest.approx(float(g["init_J"]), rel=1e-13)
+    assert rel(algo.obj_fun.eval_grad_obj_fun(X0)[:, :, 0], g["init_c"]) <= 1e-13
+    assert rel(algo.obj_fun.eval_hessian_obj_fun(X0), g["init_C"]) <= 1e-13
+    p_ref = 1 if algo._real_add_param is None else algo._real_add_param.shape[1] + 1
+    assert algo.get_obj_add_param().shape == (int(g["T"]), p_ref)          # (scenario columns, t), log_barrier_ilqr.py:96-101
+    assert algo.solve() is None
+    assert algo.inner_iterations == [int(v) for v in g["def_inner_iters"]]
+    Jreal = algo._real_obj_fun.eval_obj_fun(algo._trajectory)
+    assert Jreal == pytest.approx(float(g["def_Jreal"][-1]), rel=1e-9)
+    assert rel(algo._trajectory[:, :, 0], g["def_X"]) <= 1e-8
+
+
+@pytest.mark.parametrize("tag", BARRIER_TAGS)
+def test_barrier_seeded_batch_fused_and_per_launch(golden, tag):
+    """solve_batch: the whole schedule in one kernel (crl_solve_stages with time-varying rows) and one launch per t give
+    the same bits, and the reference's inner-loop iteration counts and trajectories."""
+    g = golden(tag)
+    a = make_barrier_algo(g).solve_batch(g["batch_x0"], fused=True)
+    b = make_barrier_algo(g).solve_batch(g["batch_x0"], fused=False)
+    for f in ("inner_iterations", "iterations", "converged", "obj_fun_value", "trajectory", "real_obj_fun_value"):
+        assert torch.equal(getattr(a, f), getattr(b, f)), f
+    # A problem with an inner loop that ran into max_iter is cut off while it is still moving (and carries its stored
+    # cost into the next loop); the reference has no noise envelope for these fixtures, so the exact bars - the
+    # reference's iteration count in EVERY inner loop, cost <= 1e-8, trajectory <= 1e-7 - apply to the problems whose
+    # loops all ended by the stopping criterion; the others must terminate normally within 10 % of the reference's work.
+    ref_inner = g["batch_inner_iters"]
+    clean = np.all(ref_inner < int(g["max_iter"]), axis=1)
+    inner = a.inner_iterations.cpu().numpy()
+    J, X = a.real_obj_fun_value.cpu().numpy(), a.trajectory.cpu().numpy()
+    for b in range(len(clean)):
+        if clean[b]:
+            assert np.array_equal(inner[b], ref_inner[b])
+            assert abs(J[b] - g["batch_Jreal"][b]) <= 1e-8 * abs(g["batch_Jreal"][b])
+            assert rel(X[b], g["batch_X"][b]) <= 1e-7
+        else:
+            assert np.isfinite(J[b]) and abs(int(inner[b].sum()) - int(ref_inner[b].sum())) <= 0.1 * ref_inner[b].sum()
+    if tag == "LogBarrierGeneric_Vehicle_T150":
+        assert clean.all()

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), "symbol %s declared in the header is not exported" % name
     assert sorted(_native.EXPORTS) == names
-    assert lib.crl_abi_version() == _native.ABI_VERSION == 5
+    assert lib.crl_abi_version() == _native.ABI_VERSION == 6
 
 
 def test_model_tables_and_status_strings():
@@ -35,7 +35,8 @@ def test_model_tables_and_status_strings():
     assert _native.model_dims(3) == (6, 2, 4) and _native.model_dims(4) == (8, 3, 4) and _native.model_dims(5) == (6, 2, 4)
     assert _native.model_default_bounds(5) == (-500.0, 500.0)
     lib = _native.load()
-    assert lib.crl_model_dims(10, None, None, None) == -2
+    assert lib.crl_model_dims(14, None, None, None) == -2
+    assert _native.model_dims(12) == (4, 2, 2) and _native.model_dims(10) == (4, 1, 7)    # generated barrier rows: (columns, t, t0)
     assert b"unsupported model" in lib.crl_status_string(-2)
     assert lib.crl_status_string(0) == b"ok"
     with pytest.raises(RuntimeError, match="unsupported model"):
@@ -66,7 +67,7 @@ def test_argument_validation_happens_before_any_cuda_call():
     opts = _native.SolverOpts(10, 1, 1e-6, 10, 0.5, 0, 0, 0, 0, 0, 0)
     dummy = ctypes.c_void_p(0x1000)
     assert lib.crl_rollout(None, dummy, None, 0, dummy, None, None) == -1
-    assert lib.crl_rollout(prob(model=10), dummy, None, 0, dummy, None, None) == -2
+    assert lib.crl_rollout(prob(model=14), dummy, None, 0, dummy, None, None) == -2
     assert lib.crl_rollout(prob(model=6, dtype=1), dummy, None, 0, dummy, None, None) == -2   # generated models are FP64 only
     assert lib.crl_rollout(prob(model=6, params_stride_t=2), dummy, None, 0, dummy, None, None) == -1   # its rows are 5 wide
     assert lib.crl_rollout(prob(model=5, dtype=1), dummy, None, 0, dummy, None, None) == -2   # barrier models are FP64 only
@@ -82,7 +83,7 @@ def test_argument_validation_happens_before_any_cuda_call():
                                 None) == -1
     assert lib.crl_backward_dense(5, 2, 0, 1, 10, dummy, dummy, dummy, dummy, dummy, None) == -2
     assert lib.crl_backward_dense(4, 1, 1, 1, 10, dummy, dummy, dummy, dummy, dummy, None) == -2   # FP64 only
-    assert lib.crl_solve_workspace_bytes(ctypes.byref(prob(model=10)), ctypes.byref(opts)) == 0
+    assert lib.crl_solve_workspace_bytes(ctypes.byref(prob(model=14)), ctypes.byref(opts)) == 0
     assert lib.crl_solve_workspace_bytes(ctypes.byref(prob(model=8, batch=33, horizon=10)), ctypes.byref(opts)) == 2 * 10 * 32 * (12 + 8 + 2) * 8
 
 

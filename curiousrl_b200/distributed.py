@@ -29,6 +29,8 @@ class GatheredResult:
     iterations: torch.Tensor       # [B] int32
     converged: torch.Tensor        # [B] uint8
     trajectory: Optional[torch.Tensor] = None   # [B, T, d] only if requested
+    inner_iterations: Optional[torch.Tensor] = None     # [B, len(t)] int32  (LogBarrieriLQR)
+    real_obj_fun_value: Optional[torch.Tensor] = None   # [B] float64         (LogBarrieriLQR: barrier-free cost)
 
 
 def _all_gather_ragged(local: torch.Tensor, counts, group=None) -> torch.Tensor:
@@ -57,15 +59,25 @@ def gather_results(obj_fun_value: torch.Tensor, iterations: torch.Tensor, conver
     return GatheredResult(J, it, cv, X)
 
 
-def solve_sharded(algo, init_state, add_param, gather_trajectory: bool = False, group=None, **kw) -> GatheredResult:
+def solve_sharded(algo, init_state, add_param=None, gather_trajectory: bool = False, group=None, **kw) -> GatheredResult:
     """Solve this rank's slice of a replicated [B, ...] problem set and gather the per-trajectory results.
 
-    `init_state` [B, n] and `add_param` [B, p] / [B, T, p] are the FULL batch (host or device);
-    only the local slice is uploaded.
+    `init_state` [B, n] and `add_param` [B, p] / [B, T, p] are the FULL batch (host or device); only the local slice
+    is uploaded.  `add_param=None`: every problem uses the scenario's own parameters (the scenarios without a target).
+    `algo` is a BasiciLQR or a LogBarrieriLQR; the latter's per-loop iteration counts and barrier-free costs are
+    gathered too (4 * len(t) + 8 more bytes per trajectory).
     """
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     B = int(init_state.shape[0])
     lo, hi = shard_range(B, rank, world)
-    res = algo.solve_batch(init_state[lo:hi], add_param[lo:hi], return_trajectory=gather_trajectory, **kw)
-    return gather_results(res.obj_fun_value, res.iterations, res.converged, B,
-                          trajectory=res.trajectory if gather_trajectory else None, group=group)
+    wants_traj = gather_trajectory or hasattr(algo, "_real_dev")      # the log-barrier solver needs them for its real cost
+    res = algo.solve_batch(init_state[lo:hi], None if add_param is None else add_param[lo:hi],
+                           return_trajectory=wants_traj, **kw)
+    out = gather_results(res.obj_fun_value, res.iterations, res.converged, B,
+                         trajectory=res.trajectory if gather_trajectory else None, group=group)
+    counts = [shard_range(B, r, world)[1] - shard_range(B, r, world)[0] for r in range(world)]
+    if getattr(res, "inner_iterations", None) is not None:
+        out.inner_iterations = _all_gather_ragged(res.inner_iterations, counts, group)
+    if getattr(res, "real_obj_fun_value", None) is not None:
+        out.real_obj_fun_value = _all_gather_ragged(res.real_obj_fun_value, counts, group)
+    return out

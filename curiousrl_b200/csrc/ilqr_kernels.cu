@@ -37,6 +37,17 @@ constexpr int kLsChunk = CRL_LS_CHUNK;   // step sizes evaluated per pass of the
 #ifndef CRL_HELP_MAX
 #define CRL_HELP_MAX 16
 #endif
+#ifndef CRL_SPLIT_ROLLOUT
+#define CRL_SPLIT_ROLLOUT 1
+#endif
+#ifndef CRL_SPLIT_UNROLL
+#define CRL_SPLIT_UNROLL 2
+#endif
+#ifndef CRL_SPLIT_MAX_LIVE
+#define CRL_SPLIT_MAX_LIVE 1
+#endif
+constexpr int kSplitMaxLive = CRL_SPLIT_MAX_LIVE;        // ... for warps that hold at most this many trajectories
+constexpr bool kSplitRollout = CRL_SPLIT_ROLLOUT != 0;   // two-phase line search for a warp's lone trajectory (coop_recurrence)
 constexpr int kHelpMax = CRL_HELP_MAX;   // after the first pass, at most this many still-searching lanes are helped by the others
 constexpr bool kHelpLs = kHelpMax > 0;
 
@@ -449,6 +460,104 @@ __device__ __noinline__ double coop_rollout(const R* X, const R* K, const R* k, 
     return rollout_closed_f<Mdl, R>(feed, alpha, prm, ub, T, RowView<R, RS>{Xnew, store});
 }
 
+// ---- two-phase rollout of a LONE trajectory (kinematic chains) ----------------------------------------------
+// In the kinematic-chain models only the joint states and the actions are on the closed-loop rollout's recurrence
+// (dx -> u -> s'); the end-effector outputs (sin / cos of the cumulative angles) and the cost terms - three quarters
+// of a step's instructions, all of the barrier cost's logarithms - depend on finished rows only.  A warp that holds a
+// single trajectory (the end of the tail, where the per-iteration latency is the critical path of the whole solve)
+// therefore splits the line search: (1) every candidate lane runs the bare recurrence and stores joint states and
+// actions; (2) all 32 lanes share the (candidate, time step) pairs: outputs of row t from the angles of row t-1, then
+// the cost of row t; (3) every candidate lane sums its per-step costs in time order.  Each value is produced by the
+// operation sequence of rollout_closed_f, so the result is bit-identical to the one-phase rollout.
+template <class Mdl, class R, int RS>
+__device__ __noinline__ void coop_recurrence(const R* X, const R* K, const R* k, R alpha, Bounds<R> ub, int T, R* Xnew) {
+    constexpr int N = Mdl::N, M = Mdl::M, NS = Mdl::NS, J = Mdl::M;
+    RowPrefetchFeed<Mdl, R, RS> feed(X, K, k);
+    R s[NS], u[M];
+    feed.begin(T - 1);
+    CRL_UNROLL for (int j = 0; j < NS; ++j) s[j] = X[j];
+    CRL_UNROLL for (int y = 0; y < N - NS; ++y) Xnew[NS + y] = X[NS + y];             // row 0 is copied whole
+    CRL_UNROLL for (int a = 0; a < M; ++a) u[a] = X[N + a];
+    for (int t = 0; t < T - 1; ++t) {
+        R xo_c[NS], uo_c[M], K_c[M * NS], k_c[M];
+        feed.get(t, xo_c, uo_c, K_c, k_c);
+        R dx[NS];
+        CRL_UNROLL for (int j = 0; j < NS; ++j) dx[j] = s[j] - xo_c[j];
+        CRL_UNROLL for (int a = 0; a < M; ++a) {
+            R acc = K_c[a * NS] * dx[0];
+            CRL_UNROLL for (int j = 1; j < NS; ++j) acc = fmadd(K_c[a * NS + j], dx[j], acc);
+            R du = acc + alpha * k_c[a];
+            u[a] = clamp_(uo_c[a] + du, ub.lo, ub.hi);
+        }
+        R* row = Xnew + (size_t)t * RS;
+        CRL_UNROLL for (int j = 0; j < NS; ++j) row[j] = s[j];
+        CRL_UNROLL for (int a = 0; a < M; ++a) row[N + a] = u[a];
+        R sn[NS];
+        CRL_UNROLL for (int j = 0; j < J; ++j) {                                     // step_trig's joint part
+            sn[2 * j] = s[2 * j] + R(kH) * s[2 * j + 1];
+            sn[2 * j + 1] = s[2 * j + 1] + R(kH) * u[j];
+        }
+        CRL_UNROLL for (int j = 0; j < NS; ++j) s[j] = sn[j];
+    }
+    if (T > 1) { CRL_UNROLL for (int a = 0; a < M; ++a) u[a] = R(0); }                // last action stays 0
+    R* row = Xnew + (size_t)(T - 1) * RS;
+    CRL_UNROLL for (int j = 0; j < NS; ++j) row[j] = s[j];
+    CRL_UNROLL for (int a = 0; a < M; ++a) row[N + a] = u[a];
+}
+
+// phases 2 and 3 for the candidates `cand_mask` (bit c = candidate c of the buffer Xbuf = [T][GL][DP]); returns this
+// lane's candidate cost (lanes c < GL of `group_lane0`'s group; 0 for the others).  Lcost: GL * T doubles of scratch.
+template <class Mdl, class R, int GL, int DP>
+__device__ __noinline__ double coop_outputs_and_costs(R* Xbuf, unsigned cand_mask, ParamRef<R> prm, int T, double* Lcost,
+                                                      int lane, int my_cand) {
+    constexpr int N = Mdl::N, D = Mdl::D, NS = Mdl::NS, RS = GL * DP;
+    const int n_cand = __popc(cand_mask);
+    const int n_items = n_cand * T;
+    // kU (candidate, time step) pairs per lane and round, all their loads issued before any of them is evaluated
+    // (the rows sit in L2 / DRAM and the stores below would otherwise fence the next pair's loads)
+    constexpr int kU = CRL_SPLIT_UNROLL;
+    for (int i0 = lane; i0 < n_items; i0 += 32 * kU) {
+        R xu[kU][D], pang[kU][NS];
+        R* row[kU];
+        int tt[kU], cc[kU];
+        bool on[kU];
+        CRL_UNROLL for (int r = 0; r < kU; ++r) {
+            const int i = i0 + 32 * r;
+            on[r] = i < n_items;
+            const int ii = on[r] ? i : lane;
+            cc[r] = (int)__fns(cand_mask, 0, ii / T + 1);
+            tt[r] = ii % T;
+            row[r] = Xbuf + (size_t)tt[r] * RS + cc[r] * DP;
+            CRL_UNROLL for (int j = 0; j < NS; ++j) xu[r][j] = __ldcg(row[r] + j);
+            CRL_UNROLL for (int a = 0; a < Mdl::M; ++a) xu[r][N + a] = __ldcg(row[r] + N + a);
+            const R* prev = tt[r] > 0 ? row[r] - RS : row[r];
+            CRL_UNROLL for (int j = 0; j < NS; ++j) pang[r][j] = __ldcg(prev + j);
+            CRL_UNROLL for (int y = NS; y < N; ++y) xu[r][y] = __ldcg(row[r] + y);          // valid for t = 0 only
+        }
+        CRL_UNROLL for (int r = 0; r < kU; ++r) {
+            if (!on[r]) continue;
+            if (tt[r] > 0) {
+                // outputs of row t = step_trig's output part at row t-1
+                R pxu[D], ang[Mdl::NANG], sn[Mdl::NANG], cs[Mdl::NANG], xn[N];
+                CRL_UNROLL for (int j = 0; j < NS; ++j) pxu[j] = pang[r][j];
+                CRL_UNROLL for (int j = NS; j < D; ++j) pxu[j] = R(0);
+                Mdl::template angles<R>(pxu, ang);
+                sincos_batch<Mdl::NANG, R>(ang, sn, cs);
+                Mdl::template step_trig<R>(pxu, sn, cs, xn);
+                CRL_UNROLL for (int y = NS; y < N; ++y) { xu[r][y] = xn[y]; row[r][y] = xn[y]; }
+            }
+            Lcost[cc[r] * T + tt[r]] = step_cost<Mdl, R>(xu[r], prm, tt[r]);
+        }
+    }
+    __syncwarp();
+    double Jc = 0.0;
+    if (my_cand >= 0 && ((cand_mask >> my_cand) & 1u)) {
+        const double* L = Lcost + (size_t)my_cand * T;
+        for (int t = 0; t < T; ++t) Jc = Jc + L[t];
+    }
+    return Jc;
+}
+
 // NT == 8: the pair-group pass (4 lanes per trajectory, kinematic chains); NT == 4: the column-group pass
 // (8 lanes per trajectory); otherwise the element-per-lane pass
 // the element-per-lane pass exists for the kinematic chains only
@@ -509,7 +618,8 @@ __host__ __device__ constexpr long long coop_xscr_reals(int T) {
 }
 template <class Mdl>
 __host__ __device__ constexpr long long coop_gscr_reals_per_traj(int T) {
-    return (long long)T * (Mdl::M * Mdl::NS + Mdl::M + Mdl::kCoopTab);
+    // K, k, the table of variable Jacobian entries, and (two-phase line search) the per-step costs of 8 candidates
+    return (long long)T * (Mdl::M * Mdl::NS + Mdl::M + Mdl::kCoopTab + 8);
 }
 template <class Mdl, int NT>
 __host__ __device__ constexpr long long coop_scratch_reals(int T) {
@@ -736,6 +846,9 @@ __device__ void coop_engine(const SolveArgs<R>& a, Source& src, R* xscr, R* gscr
         __syncwarp();
         tm.lap(PH_COOP_BACKWARD);
         // ---- line search: GL step sizes per trajectory and pass, candidates side by side in the slot's other buffer
+        // trajectories this warp holds (warp-uniform): the two-phase line search is chosen by it
+        int n_live = 0;
+        CRL_UNROLL for (int q = 0; q < NT; ++q) n_live += s_traj[q] >= 0 ? 1 : 0;
         bool accepted[NT];
         int next[NT], taken[NT], newcol[NT];
         double J_new[NT];
@@ -759,7 +872,32 @@ __device__ void coop_engine(const SolveArgs<R>& a, Source& src, R* xscr, R* gscr
             const int idx = my_next + c_ls;
             double Jt = 0.0;
             bool ok = false;
-            if (ls_lane && my_pend && idx < tries) {
+            bool split = false;
+            if constexpr (kSplitRollout && Mdl::kKinematic && Mdl::kBarrier && sizeof(R) == 8 && GL == 8)
+                split = n_live <= kSplitMaxLive;
+            if (split) {
+                // two-phase rollout (see coop_recurrence): every lane of the warp takes part in phase 2
+                const bool mine = ls_lane && my_pend && idx < tries;
+                if (mine) {
+                    double al = 1.0;
+                    for (int i = 0; i < idx; ++i) al = al * a.op.gamma;
+                    coop_recurrence<Mdl, R, RS>(mt.X, mt.K, mt.k, (R)al, a.pb.ub, T,
+                                                xscr + (size_t)(2 * q_ls + (my_buf ^ 1)) * BUF + c_ls * DP);
+                }
+                const unsigned mm = __ballot_sync(kFull, mine);
+                __syncwarp();
+                CRL_UNROLL for (int q = 0; q < NT; ++q) {
+                    const unsigned cm = (mm >> (q * GL)) & ((1u << GL) - 1u);
+                    if (cm == 0u) continue;                                          // warp-uniform
+                    double* const Lcost = reinterpret_cast<double*>(gscr + (size_t)q * TGS + TK + Tk + (size_t)T * Mdl::kCoopTab);
+                    const double Jq = coop_outputs_and_costs<Mdl, R, GL, DP>(xscr + (size_t)(2 * q + (s_buf[q] ^ 1)) * BUF, cm,
+                                                                             tr[q].prm, T, Lcost, lane,
+                                                                             (mine && q_ls == q) ? c_ls : -1);
+                    if (mine && q_ls == q) Jt = Jq;
+                }
+                __syncwarp();
+                if (mine) ok = (a.op.ls_method == CRL_LS_NONE) || ls_accept(Jt, my_Jl, feas);
+            } else if (ls_lane && my_pend && idx < tries) {
                 double al = 1.0;
                 for (int i = 0; i < idx; ++i) al = al * a.op.gamma;
                 Jt = coop_rollout<Mdl, R, RS>(mt.X, mt.K, mt.k, (R)al, mt.prm, a.pb.ub, T,

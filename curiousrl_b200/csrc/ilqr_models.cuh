@@ -36,6 +36,7 @@ template <int J>
 struct KinematicArm {
     static constexpr int NS = 2 * J, NO = 2, N = NS + NO, M = J, D = N + M, P = 2;
     static constexpr bool kBarrier = false;
+    static constexpr bool kKinematic = true;       // joint states are double integrators: no trigonometry on the rollout's recurrence
     // order in which sympy prints the per-action terms of a sum (symbol names sort as strings: x_u10 < x_u8 < x_u9)
     CRL_HD static constexpr int action_order(int k) { return J == 3 ? (k == 0 ? 2 : k - 1) : k; }
 
@@ -164,6 +165,7 @@ struct RoboticArm {
     static constexpr int ID = 2;
     static constexpr int NS = 4, NO = 2, N = 6, M = 2, D = 8, P = 2;
     static constexpr bool kBarrier = false;
+    static constexpr bool kKinematic = false;
     CRL_HD static constexpr int action_order(int k) { return k; }
     static constexpr double k1 = 0.0266666666666667, k2 = 0.0233333333333333, kden = 6.22222222222222;
 

@@ -88,7 +88,7 @@ def generate_struct(scenario) -> str:
     out = ["// %s  (n = %d, m = %d, p = %d)" % (name, n, m, p),
            "struct Gen%s {" % name,
            "    static constexpr int N = %d, M = %d, D = %d, P = %d;" % (n, m, d, p),
-           "    static constexpr int kModelId = %d;" % GENERIC_MODEL_IDS[name],
+           "    static constexpr int kModelId = %d;" % GENERIC_MODEL_IDS.get(name, -1),
            "    static constexpr bool kBarrier = false;",
            "    CRL_GEN_FN double lo(int i) { constexpr double b[D] = {%s}; return b[i]; }" % ", ".join(_fmt_bound(v) for v in constr[:, 0]),
            "    CRL_GEN_FN double hi(int i) { constexpr double b[D] = {%s}; return b[i]; }" % ", ".join(_fmt_bound(v) for v in constr[:, 1]),
@@ -131,7 +131,7 @@ def generate_barrier_struct(scenario) -> str:
            "struct Gen%sBarrier : Gen%s {" % (name, name),
            "    static constexpr int P = %d;" % (len(pv) + 2),
            "    static constexpr int kT = %d;                   // index of t in the parameter row; t0 follows" % len(pv),
-           "    static constexpr int kModelId = %d;" % GENERIC_BARRIER_MODEL_IDS[name],
+           "    static constexpr int kModelId = %d;" % GENERIC_BARRIER_MODEL_IDS.get(name, -1),
            "    static constexpr bool kBarrier = true;",
            "    CRL_GEN_FN double cost(const double* x, const double* p) {"]
     out += ax + ap + ["        return %s;" % printer.doprint(sp.sympify(l))]

@@ -5,11 +5,14 @@
 
 What is generated per scenario (a struct `Gen<ClassName>` used by csrc/ilqr_generic.cuh):
 
-    N, M, D, P, kLo[D], kHi[D]              sizes and the box `constr`
+    N, M, D, P, lo(i), hi(i)                sizes and the box `constr`
     step(xu, xn)                            x_{t+1} = f(x_t, u_t)              scenario.dynamic_function
     jac(xu, F[N*D])                         transpose(derive_by_array(f, xu))  ilqr_dynamic_model.py:35
     cost(xu, p) / grad(xu, p, c[D])         l, derive_by_array(l, xu)          ilqr_obj_fun.py:46-48
     hess(xu, p, C[D*D])                     d^2 l + 1e-100 I                   ilqr_obj_fun.py:49-51
+
+and a struct `Gen<ClassName>Barrier : Gen<ClassName>` with cost / grad / hess of LogBarrieriLQR's objective
+(log_barrier_ilqr.py:84-101: every finite bound adds a (-1/t) log term; parameter row = the scenario's columns, t, t0).
 
 Every expression is differentiated and printed on its own, term order as sympy prints it, WITHOUT common
 sub-expression elimination - the reference evaluates the code `sympy.lambdify` prints for exactly these

@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int
 
 from . import build as _build
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MODEL_IDS = {"TwoLinkPlanarManipulator": 0, "ThreeLinkPlanarManipulator": 1, "RoboticArmTracking": 2}
 # the same scenarios under LogBarrieriLQR's cost (include/curiousrl_b200.h: CRL_*_BARRIER); FP64 only
 BARRIER_MODEL_IDS = {name: mid + 3 for name, mid in MODEL_IDS.items()}
@@ -31,7 +31,7 @@ EXPORTS = ("crl_abi_version", "crl_status_string", "crl_model_dims", "crl_model_
 class Problem(Structure):
     _fields_ = [("model", c_int32), ("dtype", c_int32), ("batch", c_int64), ("horizon", c_int32),
                 ("params_stride_t", c_int32), ("params_stride_b", c_int64), ("params", c_void_p),
-                ("u_lo", c_double), ("u_hi", c_double)]
+                ("u_lo", c_double), ("u_hi", c_double), ("bounds_host", c_void_p)]
 
 
 class SolverOpts(Structure):

@@ -40,7 +40,7 @@ class BatchResult:
 
 class DeviceModel:
     def __init__(self, model_name: str, T: int, u_lo: float, u_hi: float, dtype: str = "float64", device=None,
-                 barrier: bool = False):
+                 barrier: bool = False, bounds=None):
         self.generic = model_name in _native.GENERIC_MODEL_IDS      # generated device model: FP64, bounds compiled in
         if model_name not in _native.MODEL_IDS and not self.generic:
             raise Exception('Scenario "%s" has no device model in curiousrl_b200 (supported: %s); '
@@ -63,6 +63,10 @@ class DeviceModel:
         self.T = int(T)
         self.dtype_name, self.dtype, self.dtype_id = dtype, _TORCH_DTYPE[dtype], _native.DTYPE_IDS[dtype]
         self.u_lo, self.u_hi = float(u_lo), float(u_hi)
+        # generated models: the box `constr` [d, 2] if it is not the scenario's default (host array, read by every call)
+        self._bounds = None if bounds is None else np.ascontiguousarray(bounds, dtype=np.float64).reshape(self.d, 2)
+        if self._bounds is not None and not self.generic:
+            raise ValueError("per-component bounds are for the generated models")
         self._workspace = None
         self.launches = 0          # kernels enqueued through this object (bench accounting)
 
@@ -95,7 +99,11 @@ class DeviceModel:
             raise ValueError("add_param must have 1, 2 or 3 dimensions")
         if params.shape[-1] != self.p:
             raise ValueError("add_param last dimension must be %d" % self.p)
-        return _native.Problem(self.model_id, self.dtype_id, B, self.T, st, sb, params.data_ptr(), self.u_lo, self.u_hi)
+        return _native.Problem(self.model_id, self.dtype_id, B, self.T, st, sb, params.data_ptr(), self.u_lo, self.u_hi,
+                               self._bounds_ptr())
+
+    def _bounds_ptr(self):
+        return None if self._bounds is None else self._bounds.ctypes.data
 
     def _u0(self, u0, B):
         """None -> zeros; [T, m] shared; [B, T, m] per trajectory.  Returns (tensor-or-None, batch stride)."""
@@ -248,7 +256,8 @@ class DeviceModel:
         per_b = S * self.p * (self.T if stage_params.dim() == 4 else 1)
         sb = 0 if (stage_params.shape[0] == 1 and B != 1) else per_b
         st = self.p if stage_params.dim() == 4 else 0
-        prob = _native.Problem(self.model_id, self.dtype_id, B, self.T, st, sb, stage_params.data_ptr(), self.u_lo, self.u_hi)
+        prob = _native.Problem(self.model_id, self.dtype_id, B, self.T, st, sb, stage_params.data_ptr(), self.u_lo, self.u_hi,
+                               self._bounds_ptr())
         u0t, u0s = self._u0(u0, B)
         ws = self.workspace(prob, opts)
         if J_init is not None:

@@ -259,11 +259,12 @@ class BasiciLQR(iLQRWrapper):
         T = int(scenario.init_action.shape[0])
         if scenario.name in _native.GENERIC_MODEL_IDS:
             # generated device model: the whole box - state bounds included - is compiled in
+            # the scenario's default box is compiled in; any other one (is_with_constraints=False) is passed per call
             compiled = np.asarray(_native.model_bounds(_native.GENERIC_MODEL_IDS[scenario.name]), dtype=np.float64)
-            if compiled.shape != constr.shape or not np.array_equal(compiled, constr):
-                raise Exception('Scenario "%s": the device model is generated for constr = %s (is_with_constraints=True); '
-                                "there is no CPU fallback." % (scenario.name, compiled.tolist()))
-            self._dev = DeviceModel(scenario.name, T, 0.0, 0.0, dtype=self._dtype, device=self._device)
+            if compiled.shape != constr.shape:
+                raise Exception('Scenario "%s" does not have the shape of the device model' % scenario.name)
+            self._dev = DeviceModel(scenario.name, T, 0.0, 0.0, dtype=self._dtype, device=self._device,
+                                    bounds=None if np.array_equal(compiled, constr) else constr)
         else:
             if not (np.all(constr[:n, 0] == -np.inf) and np.all(constr[:n, 1] == np.inf)):
                 raise Exception('Scenario "%s": finite state bounds are not supported by the device models' % scenario.name)

@@ -24,11 +24,20 @@ struct GenProblemDev {
     int stride_t;
     long long B;
     int T;
-    __device__ GenParams prm(long long b) const { return GenParams{params + b * stride_b, stride_t}; }
+    GenBox box;
+    __device__ GenParams prm(long long b) const { return GenParams{params + b * stride_b, stride_t, box}; }
 };
 
+// the scenario's default box, or the caller's (crl_problem::bounds_host, [d][2] rows of (lo, hi) in host memory)
 GenProblemDev to_gen(const crl_problem_t* p) {
-    return GenProblemDev{(const double*)p->params, p->params_stride_b, p->params_stride_t, p->batch, p->horizon};
+    GenProblemDev d{(const double*)p->params, p->params_stride_b, p->params_stride_t, p->batch, p->horizon, GenBox{}};
+    int n = 0, m = 0;
+    gen_dims(p->model, &n, &m, nullptr);
+    gen_bounds(p->model, d.box.lo, d.box.hi);
+    if (p->bounds_host) {
+        for (int i = 0; i < n + m; ++i) { d.box.lo[i] = p->bounds_host[2 * i]; d.box.hi[i] = p->bounds_host[2 * i + 1]; }
+    }
+    return d;
 }
 GenOpts to_gen(const crl_solver_opts_t* o) {
     return GenOpts{o->max_iter, o->is_check_stop, o->max_line_search, o->line_search_method, o->stopping_method,

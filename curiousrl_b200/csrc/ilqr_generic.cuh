@@ -20,19 +20,32 @@
 
 namespace crl {
 
+// The box `constr` of a problem, component by component (states first).  The generated models carry the scenario's
+// default box (G::lo / G::hi); a caller may pass another one (e.g. is_with_constraints=False: all +-inf).
+struct GenBox {
+    double lo[8], hi[8];
+};
+template <class G>
+CRL_HD GenBox gen_default_box() {
+    static_assert(G::D <= 8, "GenBox holds up to 8 components");
+    GenBox b;
+    for (int i = 0; i < 8; ++i) { b.lo[i] = i < G::D ? G::lo(i) : 0.0; b.hi[i] = i < G::D ? G::hi(i) : 0.0; }
+    return b;
+}
+
 // min(max(lo, v), hi) with Python's semantics (ilqr_dynamic_model.py:107-108, :127-128, :130-131): max(a, b) is
 // "b if b > a else a", min(a, b) is "b if b < a else a" - so a NaN is replaced by the lower bound, as in the reference.
-template <class G>
-CRL_HD double gen_clamp(double v, int i) {
-    const double lo = G::lo(i), hi = G::hi(i);
+CRL_HD double gen_clamp(double v, int i, const GenBox& box) {
+    const double lo = box.lo[i], hi = box.hi[i];
     const double w = v > lo ? v : lo;
     return hi < w ? hi : w;
 }
 
-// Parameter row of time step t: p(t, i) = ptr[t * stride_t + i]
+// Parameter row of time step t: p(t, i) = ptr[t * stride_t + i]; the problem's box rides along.
 struct GenParams {
     const double* ptr;
     int stride_t;
+    GenBox box;
     template <int P>
     CRL_HD void load(int t, double (&p)[P]) const {
         for (int i = 0; i < P; ++i) p[i] = ptr[(size_t)t * stride_t + i];
@@ -51,7 +64,7 @@ CRL_HD double gen_rollout_open(const double* x0, const double* U, int su_t, GenP
         const bool last = (t == T - 1);
         if (!last) {
             G::step(xu, xn);                                                   // from the UNclamped row
-            for (int i = 0; i < D; ++i) xu[i] = gen_clamp<G>(xu[i], i);        // row t clamped afterwards
+            for (int i = 0; i < D; ++i) xu[i] = gen_clamp(xu[i], i, prm.box);   // row t clamped afterwards
         }
         double* row = X.row(t);
         for (int i = 0; i < D; ++i) X.st(row, i, xu[i]);
@@ -155,7 +168,7 @@ CRL_HD double gen_rollout_closed(XV X, KV K, SV k, double alpha, GenParams prm, 
                 double acc = Kc[a * N + 0] * dx[0];
                 for (int j = 1; j < N; ++j) acc = fmadd(Kc[a * N + j], dx[j], acc);
                 const double du = acc + alpha * kc[a];
-                xu[N + a] = gen_clamp<G>(xo[N + a] + du, N + a);
+                xu[N + a] = gen_clamp(xo[N + a] + du, N + a, prm.box);
             }
             G::step(xu, xn);
         } else {
@@ -166,7 +179,7 @@ CRL_HD double gen_rollout_closed(XV X, KV K, SV k, double alpha, GenParams prm, 
         prm.load(t, p);
         J = J + G::cost(xu, p);
         if (!last) {
-            for (int i = 0; i < N; ++i) xu[i] = gen_clamp<G>(xn[i], i);        // state clamp after the dynamics
+            for (int i = 0; i < N; ++i) xu[i] = gen_clamp(xn[i], i, prm.box);   // state clamp after the dynamics
         }
     }
     return J;
@@ -193,7 +206,8 @@ CRL_HD void gen_solve_one(const double* x0, const double* U, int su_t, GenParams
     int total = 0;
     bool stopped = false;
     for (int s = 0; s < n_stage; ++s) {
-        const GenParams ps{prm.ptr + (size_t)s * stage_stride, prm.stride_t};
+        GenParams ps = prm;
+        ps.ptr = prm.ptr + (size_t)s * stage_stride;
         if (s > 0 && stopped) J_last = (double)INFINITY;                       // log_barrier_ilqr.py:141
         int it = 0;
         stopped = false;

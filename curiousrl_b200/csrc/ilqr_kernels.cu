@@ -1425,6 +1425,17 @@ static int check_problem(const crl_problem_t* p) {
         if (p->dtype != CRL_F64) return CRL_ERR_UNSUPPORTED_MODEL;
         if (p->batch < 0 || p->horizon < 1 || (p->batch > 0 && !p->params)) return CRL_ERR_BAD_ARGUMENT;
         if ((p->params_stride_t != 0 && p->params_stride_t != pw) || p->params_stride_b < 0) return CRL_ERR_BAD_ARGUMENT;
+        if (p->bounds_host) {
+            int n = 0, m = 0;
+            double lo[8], hi[8];
+            gen_dims(p->model, &n, &m, nullptr);
+            gen_bounds(p->model, lo, hi);
+            for (int i = 0; i < n + m; ++i) {
+                const double bl = p->bounds_host[2 * i], bh = p->bounds_host[2 * i + 1];
+                if (!(bl <= bh)) return CRL_ERR_BAD_ARGUMENT;
+                if (gen_is_barrier(p->model) && (bl != lo[i] || bh != hi[i])) return CRL_ERR_UNSUPPORTED_MODEL;
+            }
+        }
         return CRL_OK;
     }
     if (p->model < CRL_TWO_LINK || p->model > CRL_ROBOTIC_ARM_BARRIER) return CRL_ERR_UNSUPPORTED_MODEL;

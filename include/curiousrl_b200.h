@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CRL_ABI_VERSION 6
+#define CRL_ABI_VERSION 7
 
 typedef void* crl_stream_t; /* cudaStream_t */
 
@@ -82,6 +82,10 @@ typedef struct crl_problem {
     int64_t params_stride_b;  /* elements between trajectories of `params` (0 = shared)       */
     const void* params;       /* [B][T][p] (or broadcast per the strides)                     */
     double u_lo, u_hi;        /* action bounds, same for every action; +-inf = unconstrained  */
+    const double* bounds_host; /* generated models (CRL_GEN_*) only, HOST memory, read during the call: the box
+                                  `constr` as [d][2] rows of (lo, hi), states first - e.g. all +-inf for
+                                  is_with_constraints=False; NULL = the scenario's default box (crl_model_bounds).
+                                  The barrier variants are generated for the default box: NULL or equal to it.   */
 } crl_problem_t;
 
 /* BasiciLQR constructor arguments (basic_ilqr.py:13-20).                                      */

@@ -43,6 +43,14 @@ class GenericHostSim:
         self.n, self.m, self.p = n.value, m.value, p.value
         self.d = self.n + self.m
 
+    def set_box(self, constr=None):
+        """Box of the following calls ([d, 2] rows of (lo, hi)); None = the model's default."""
+        if constr is None:
+            lib().hg_set_box(None, 0)
+        else:
+            rows = _f64(constr).reshape(self.d, 2)
+            lib().hg_set_box(_p(rows), self.d)
+
     def bounds(self):
         lo, hi = np.zeros(self.d), np.zeros(self.d)
         assert lib().hg_bounds(self.mid, _p(lo), _p(hi)) == 0

@@ -9,6 +9,20 @@
 
 using namespace crl;
 
+namespace {
+bool g_box_on = false;
+GenBox g_box;
+template <class G>
+GenParams hp(const double* params, int stride_t) {
+    return GenParams{params, stride_t, g_box_on ? g_box : gen_default_box<G>()};
+}
+}  // namespace
+// the box of the following calls: n_comp (lo, hi) rows, or n_comp = 0 for the model's default
+extern "C" void hg_set_box(const double* rows, int n_comp) {
+    g_box_on = n_comp > 0;
+    for (int i = 0; i < 8; ++i) { g_box.lo[i] = i < n_comp ? rows[2 * i] : 0.0; g_box.hi[i] = i < n_comp ? rows[2 * i + 1] : 0.0; }
+}
+
 #define HG_DISPATCH(model, ...)                                                     \
     switch (model) {                                                                \
         case 6: { using G = GenCartPoleSwingUp1; __VA_ARGS__; } break;              \
@@ -32,7 +46,7 @@ extern "C" int hg_bounds(int model, double* lo, double* hi) {
 }
 extern "C" int hg_rollout(int model, const double* x0, const double* u0, const double* params, int stride_t, int T,
                           double* X, double* J) {
-    HG_DISPATCH(model, *J = (gen_rollout_open<G>(x0, u0, G::M, GenParams{params, stride_t}, T, View<double, G::D, 1>{X})));
+    HG_DISPATCH(model, *J = (gen_rollout_open<G>(x0, u0, G::M, hp<G>(params, stride_t), T, View<double, G::D, 1>{X})));
     return 0;
 }
 extern "C" int hg_derivs(int model, const double* X, const double* params, int stride_t, int T, double* F, double* c,
@@ -40,7 +54,7 @@ extern "C" int hg_derivs(int model, const double* X, const double* params, int s
     HG_DISPATCH(model, {
         for (int t = 0; t < T; ++t) {
             double p[G::P];
-            GenParams{params, stride_t}.load(t, p);
+            hp<G>(params, stride_t).load(t, p);
             gen_derivs<G>(X + (size_t)t * G::D, p, F + (size_t)t * G::N * G::D, c + (size_t)t * G::D,
                           C + (size_t)t * G::D * G::D);
         }
@@ -48,7 +62,7 @@ extern "C" int hg_derivs(int model, const double* X, const double* params, int s
     return 0;
 }
 extern "C" int hg_backward(int model, const double* X, const double* params, int stride_t, int T, double* K, double* k) {
-    HG_DISPATCH(model, (gen_backward<G>(View<double, G::D, 1>{const_cast<double*>(X)}, GenParams{params, stride_t}, T,
+    HG_DISPATCH(model, (gen_backward<G>(View<double, G::D, 1>{const_cast<double*>(X)}, hp<G>(params, stride_t), T,
                                         View<double, G::M * G::N, 1>{K}, View<double, G::M, 1>{k})));
     return 0;
 }
@@ -57,7 +71,7 @@ extern "C" int hg_update(int model, const double* X, const double* K, const doub
     HG_DISPATCH(model, *J = (gen_rollout_closed<G>(View<double, G::D, 1>{const_cast<double*>(X)},
                                                    View<double, G::M * G::N, 1>{const_cast<double*>(K)},
                                                    View<double, G::M, 1>{const_cast<double*>(k)}, alpha,
-                                                   GenParams{params, stride_t}, T, View<double, G::D, 1>{Xn})));
+                                                   hp<G>(params, stride_t), T, View<double, G::D, 1>{Xn})));
     return 0;
 }
 extern "C" int hg_solve(int model, const double* x0, const double* u0, const double* params, int stride_t, int T,
@@ -68,7 +82,7 @@ extern "C" int hg_solve(int model, const double* x0, const double* u0, const dou
         std::vector<double> xa((size_t)T * G::D), xb((size_t)T * G::D), Kb((size_t)T * G::M * G::N), kb((size_t)T * G::M);
         GenOpts op{max_iter, check_stop, max_ls, ls_method, stop_method, criterion, gamma};
         bool in_a = true;
-        gen_solve_one<G>(x0, u0, G::M, GenParams{params, stride_t}, T, op, J_init, View<double, G::D, 1>{xa.data()},
+        gen_solve_one<G>(x0, u0, G::M, hp<G>(params, stride_t), T, op, J_init, View<double, G::D, 1>{xa.data()},
                          View<double, G::D, 1>{xb.data()}, View<double, G::M * G::N, 1>{Kb.data()},
                          View<double, G::M, 1>{kb.data()}, J_out, iters_out, conv_out, &in_a, J_trace, alpha_trace, n_stage,
                          stage_stride, stage_iters);

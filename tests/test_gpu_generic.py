@@ -124,11 +124,9 @@ def test_large_batch_properties():
     assert torch.equal(res.trajectory[:, -1, 4:], torch.zeros_like(res.trajectory[:, -1, 4:]))     # last action stays 0
 
 
-def test_unconstrained_variant_and_other_solvers_raise():
+def test_unsupported_combinations_raise():
     import curiousrl_b200.scenario.dynamic_model as models
     from curiousrl_b200.algorithm.ilqr_solver import BasiciLQR, LogBarrieriLQR
-    with pytest.raises(Exception, match="generated for constr"):
-        BasiciLQR().init(models.VehicleTracking(is_with_constraints=False, T=20))
     with pytest.raises(Exception, match="generated for constr"):
         LogBarrieriLQR().init(models.VehicleTracking(is_with_constraints=False, T=20))
     with pytest.raises(Exception):
@@ -195,3 +193,28 @@ def test_barrier_seeded_batch_fused_and_per_launch(golden, tag):
             assert np.isfinite(J[b]) and abs(int(inner[b].sum()) - int(ref_inner[b].sum())) <= 0.1 * ref_inner[b].sum()
     if tag == "LogBarrierGeneric_Vehicle_T150":
         assert clean.all()
+
+
+@pytest.mark.parametrize("name,T", [("VehicleTracking", 40), ("CartPoleSwingUp1", 60)])
+def test_unconstrained_variant_against_the_oracle(name, T):
+    """is_with_constraints=False (every bound +-inf): the box is passed per call (crl_problem::bounds_host) instead of the
+    compiled-in default.  Checked against the CPU oracle on the same scenario object: same iteration count and accepted
+    steps, cost <= 1e-9, trajectory <= 1e-8 - and, where the bounds are active, a result different from the constrained scenario's."""
+    import curiousrl_b200.scenario.dynamic_model as models
+    from curiousrl_b200 import logger
+    from curiousrl_b200.algorithm.ilqr_solver import BasiciLQR
+    from oracle import ilqr_numpy as orc                      # checker only
+    logger.set_level(45)
+    sc = getattr(models, name)(is_with_constraints=False, T=T)
+    algo = BasiciLQR(max_line_search=10, max_iter=60).init(sc)
+    algo.solve()
+    res = algo.last_result.to_host()
+    ref = orc.solve(orc.Problem(sc, use_numba=True), None, None, max_line_search=10, max_iter=60)
+    it = ref["iters"]
+    assert int(res.iterations[0]) == it and np.array_equal(res.alpha_trace[0, :it], ref["alphas"])
+    assert abs(res.obj_fun_value[0] - ref["J"]) <= 1e-9 * abs(ref["J"])
+    assert rel(res.trajectory[0], ref["X"]) <= 1e-8
+    if name == "CartPoleSwingUp1":                           # its bounds are active (the vehicle's are not at T = 40)
+        boxed = BasiciLQR(max_line_search=10, max_iter=60).init(getattr(models, name)(T=T))
+        boxed.solve()
+        assert boxed.get_obj_fun_value() != algo.get_obj_fun_value()

@@ -76,6 +76,16 @@ def test_argument_validation_happens_before_any_cuda_call():
     assert lib.crl_rollout(prob(batch=-1), dummy, None, 0, dummy, None, None) == -1
     assert lib.crl_rollout(prob(params_stride_t=3), dummy, None, 0, dummy, None, None) == -1
     assert lib.crl_rollout(prob(u_lo=1.0, u_hi=-1.0), dummy, None, 0, dummy, None, None) == -1
+    # generated models: a caller-supplied box (host array [d][2]) is validated; the barrier variants take the default only
+    box = np.array([[-np.inf, np.inf]] * 4 + [[-2.0, 2.0]], dtype=np.float64)
+    bad = np.array([[-np.inf, np.inf]] * 4 + [[2.0, -2.0]], dtype=np.float64)
+    gen = dict(model=6, params_stride_t=5, params_stride_b=0)
+    g_ok = _native.Problem(6, 0, 4, 10, 5, 0, 0x1000, 0.0, 0.0, box.ctypes.data)
+    g_bad = _native.Problem(6, 0, 4, 10, 5, 0, 0x1000, 0.0, 0.0, bad.ctypes.data)
+    g_bar = _native.Problem(10, 0, 4, 10, 7, 0, 0x1000, 0.0, 0.0, box.ctypes.data)
+    assert lib.crl_solve_workspace_bytes(ctypes.byref(g_ok), ctypes.byref(opts)) > 0
+    assert lib.crl_rollout(g_bad, dummy, None, 0, dummy, None, None) == -1
+    assert lib.crl_rollout(g_bar, dummy, None, 0, dummy, None, None) == -2
     assert lib.crl_rollout(prob(batch=0), None, None, 0, None, None, None) == 0          # empty batch: nothing to do
     assert lib.crl_rollout(prob(), None, None, 0, dummy, None, None) == -1               # missing x0
     bad_opts = _native.SolverOpts(10, 1, 1e-6, 10, 0.5, 7, 0, 0, 0, 0, 0)

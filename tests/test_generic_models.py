@@ -183,3 +183,35 @@ def test_barrier_device_math(golden, tag):
                  line_search_method=1, stages=stages)
     assert r["inner_iters"].tolist() == g["def_inner_iters"].tolist()
     assert rel(r["X"], g["def_X"]) <= 1e-8
+
+
+# ----------------------------------------------------------------------------- edge cases: tiny horizons
+@pytest.mark.parametrize("name", ["CartPoleSwingUp1", "CartPoleSwingUp2", "VehicleTracking", "CarParking"])
+@pytest.mark.parametrize("T", [1, 2, 5])
+def test_tiny_horizons_against_the_oracle(name, T):
+    """T = 1 (no dynamics step at all: the initial row is never clamped and its action is kept), T = 2 and T = 5:
+    the device math against the oracle (plain NumPy substrate) from perturbed initial states - rollout, one closed-loop
+    update and the whole solve."""
+    from curiousrl_b200.utils.synthetic import synthetic_init_states
+    import curiousrl_b200.scenario.dynamic_model as models
+    sc = getattr(models, name)(T=T)
+    prob = orc.Problem(sc, use_numba=False)
+    hs = GenericHostSim(name)
+    P = prob.params()
+    for x0 in synthetic_init_states(sc, 3, seed=11, spread=0.3):
+        X_ref = orc.rollout(prob, x0)
+        X, J = hs.rollout(x0, sc.add_param, T)
+        assert rel(X, X_ref) <= 1e-13 and abs(J - orc.cost(prob, X_ref, P)) <= 1e-12 * max(1.0, abs(J))
+        F, c, C = orc.derivs(prob, X_ref, P)
+        K_ref, k_ref = orc.backward(prob, F, c, C)
+        K, k = hs.backward(X_ref, sc.add_param)
+        assert np.allclose(K, K_ref, rtol=1e-9, atol=1e-12) and np.allclose(k, k_ref, rtol=1e-9, atol=1e-12)
+        Xn_ref = orc.update_traj(prob, X_ref, K_ref, k_ref, 0.5)
+        Xn, _ = hs.update(X_ref, K_ref, k_ref, 0.5, sc.add_param)
+        assert np.allclose(Xn, Xn_ref, rtol=1e-12, atol=1e-13, equal_nan=True)
+        r_ref = orc.solve(prob, x0, None, max_line_search=10, max_iter=20)
+        r = hs.solve(x0, sc.add_param, T, max_iter=20, max_line_search=10)
+        assert r["iters"] == r_ref["iters"] and np.array_equal(r["alphas"], r_ref["alphas"])
+        assert abs(r["J"] - r_ref["J"]) <= 1e-9 * max(1.0, abs(r_ref["J"]))
+        if T == 1:
+            assert np.array_equal(r["X"][0, :hs.n], x0)                 # nothing moves and nothing is clamped

@@ -218,3 +218,26 @@ def test_unconstrained_variant_against_the_oracle(name, T):
         boxed = BasiciLQR(max_line_search=10, max_iter=60).init(getattr(models, name)(T=T))
         boxed.solve()
         assert boxed.get_obj_fun_value() != algo.get_obj_fun_value()
+
+
+@pytest.mark.parametrize("name", ["CartPoleSwingUp1", "VehicleTracking", "CarParking"])
+@pytest.mark.parametrize("T", [1, 2, 5])
+def test_tiny_horizons(name, T):
+    """T = 1, 2, 5 on a batch that does not fill a warp: every problem against the CPU oracle (plain NumPy substrate)."""
+    import curiousrl_b200.scenario.dynamic_model as models
+    from curiousrl_b200 import logger
+    from curiousrl_b200.algorithm.ilqr_solver import BasiciLQR
+    from curiousrl_b200.utils.synthetic import synthetic_init_states
+    from oracle import ilqr_numpy as orc                      # checker only
+    logger.set_level(45)
+    sc = getattr(models, name)(T=T)
+    algo = BasiciLQR(max_line_search=10, max_iter=20).init(sc)
+    x0 = synthetic_init_states(sc, 5, seed=11, spread=0.3)
+    res = algo.solve_batch(x0, trace=True).to_host()
+    prob = orc.Problem(sc, use_numba=False)
+    for b in range(5):
+        ref = orc.solve(prob, x0[b], None, max_line_search=10, max_iter=20)
+        it = ref["iters"]
+        assert int(res.iterations[b]) == it and np.array_equal(res.alpha_trace[b, :it], ref["alphas"])
+        assert abs(res.obj_fun_value[b] - ref["J"]) <= 1e-9 * max(1.0, abs(ref["J"]))
+        assert np.allclose(res.trajectory[b], ref["X"], rtol=1e-9, atol=1e-10)

@@ -148,7 +148,7 @@ def _stage_rows(sc, t_list, T):
                      for s in range(len(t_list))])
 
 
-@pytest.mark.parametrize("tag", BARRIER_TAGS[:2])
+@pytest.mark.parametrize("tag", BARRIER_TAGS)
 def test_barrier_oracle_is_bit_exact(golden, tag):
     """oracle.solve_log_barrier on the scenarios with state bounds / without add_param against the unmodified reference."""
     g = golden(tag)

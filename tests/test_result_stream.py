@@ -97,3 +97,36 @@ def test_logger_batch_channel(tmp_path, monkeypatch):
     finally:
         lg.set_is_use_logger(saved[1])
         lg.IS_SAVE_JSON, lg.FOLDER_NAME, lg.memory_batch = saved[0], saved[2], saved[3]
+
+
+def test_round_trip_property(tmp_path):
+    """Property test: any sequence of records with arbitrary batch sizes, trailing shapes and dtypes reads back bit for bit,
+    in order, under both addressing modes (index and -1 = last)."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    import itertools
+    counter = itertools.count()
+    dtypes = st.sampled_from([np.float64, np.float32, np.int32, np.uint8])
+    shape_tail = st.lists(st.integers(1, 4), min_size=0, max_size=2)
+    record = st.tuples(st.integers(1, 6), st.lists(st.tuples(shape_tail, dtypes), min_size=1, max_size=3))
+
+    @settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(st.lists(record, min_size=1, max_size=4), st.integers(0, 2 ** 31 - 1))
+    def check(records, seed):
+        rng = np.random.default_rng(seed)
+        stream = ResultStream("prop_%d" % next(counter), root=str(tmp_path))
+        written = []
+        for B, fields in records:
+            arrays = {"f%d" % i: (rng.standard_normal((B, *tail)) * 100).astype(dt) for i, (tail, dt) in enumerate(fields)}
+            stream.append(meta={"B": B}, **arrays)
+            written.append(arrays)
+        assert len(stream) == len(written)
+        for k, arrays in enumerate(written):
+            got = stream.read(k)
+            assert got["meta"] == {"B": next(iter(arrays.values())).shape[0]}
+            for name, a in arrays.items():
+                assert got[name].dtype == a.dtype and got[name].shape == a.shape and np.array_equal(got[name], a)
+        last = stream.read(-1)
+        for name, a in written[-1].items():
+            assert np.array_equal(last[name], a)
+
+    check()

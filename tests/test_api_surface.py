@@ -127,3 +127,29 @@ def test_log_barrier_constructor_matches_reference():
     for name in ("init", "solve", "forward_pass", "backward_pass", "set_init_state", "set_obj_add_param", "get_obj_add_param",
                  "set_obj_fun_value", "get_obj_fun_value", "solve_batch"):
         assert callable(getattr(LogBarrieriLQR, name))
+
+
+def test_cart_pole_and_vehicle_scenarios_have_the_reference_surface():
+    """The scenario classes behind the generated device models: sizes, box, initial state and cost-parameter schedules
+    of the reference classes (cart_pole_swingup1.py:16-55, cart_pole_swingup2.py:16-59, vehicle_tracking.py:15-46,
+    car_parking.py:23-73), and the unconstrained variants."""
+    import numpy as np
+    import curiousrl_b200.scenario.dynamic_model as models
+    spec = {"CartPoleSwingUp1": (4, 1, 150, 5), "CartPoleSwingUp2": (5, 1, 150, 6), "VehicleTracking": (4, 2, 150, None),
+            "CarParking": (4, 2, 500, 2)}
+    for name, (n, m, T, p) in spec.items():
+        sc = getattr(models, name)()
+        assert (sc.name, sc.n, sc.m, sc.T) == (name, n, m, T)
+        assert sc.init_state.shape == (n, 1) and sc.init_action.shape == (T, m, 1) and not sc.init_action.any()
+        assert sc.constr.shape == (n + m, 2) and len(sc.x_u_var) == n + m and len(sc.dynamic_function) == n
+        assert sc.with_model() and not sc.is_action_discrete() and not sc.is_output_image()
+        if p is None:
+            assert sc.add_param is None and sc.add_param_var is None
+        else:
+            assert sc.add_param.shape == (T, p) and len(sc.add_param_var) == p
+            assert np.all(sc.add_param[:-1] == sc.add_param[0]) and not np.array_equal(sc.add_param[-1], sc.add_param[0])
+        free = getattr(models, name)(is_with_constraints=False, T=7)
+        assert free.T == 7 and np.all(np.isinf(free.constr))
+    assert np.array_equal(models.CartPoleSwingUp1().constr[2], [-1.0, 1.0])          # the cart position is bounded
+    assert np.array_equal(models.CarParking().constr[0], [-1.0, np.inf])             # the wall
+    assert np.array_equal(models.VehicleTracking().constr[4:], [[-0.6, 0.6], [-3.0, 3.0]])

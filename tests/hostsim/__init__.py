@@ -104,10 +104,24 @@ class HostSim:
         c = np.ascontiguousarray(c, dtype=self.np)
         C = np.ascontiguousarray(C, dtype=self.np)
         T = F.shape[0]
-        K = np.zeros((T, self.m, self.n), dtype=self.np)
-        k = np.zeros((T, self.m), dtype=self.np)
-        assert self._fn("backward_dense")(self.n, self.m, _p(F), _p(c), _p(C), T, _p(K), _p(k)) == 0
+        n0, d0 = F.shape[1], F.shape[2]                   # any (n, m) the dense recursion is compiled for
+        K = np.zeros((T, d0 - n0, n0), dtype=self.np)
+        k = np.zeros((T, d0 - n0), dtype=self.np)
+        n, m = C.shape[-1] - K.shape[1], K.shape[1]
+        assert self._fn("backward_dense")(n, m, _p(F), _p(c), _p(C), T, _p(K), _p(k)) == 0
         return K, k
+
+    def riccati_step(self, xu, p, V, v):
+        """One structured Riccati step (the solve kernel's riccati_step) from the value function (V [n,n], v [n]) of the
+        next time step; returns K [m,n], k [m] and the new (V, v)."""
+        xu = np.ascontiguousarray(xu, dtype=self.np).reshape(-1)
+        p = np.ascontiguousarray(p, dtype=self.np).reshape(-1)
+        V = np.array(V, dtype=self.np).reshape(self.n, self.n).copy()
+        v = np.array(v, dtype=self.np).reshape(self.n).copy()
+        K = np.zeros((self.m, self.n), dtype=self.np)
+        k = np.zeros(self.m, dtype=self.np)
+        assert self._fn("riccati_step")(self.mid, _p(xu), _p(p), _p(V), _p(v), _p(K), _p(k)) == 0
+        return K, k, V, v
 
     def solve(self, x0, target, T, max_iter=1000, is_check_stop=True, stopping_criterion=1e-6, max_line_search=10,
               gamma=0.5, line_search_method=0, stopping_method=0, J_init=np.inf, u0=None):

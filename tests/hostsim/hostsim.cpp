@@ -48,6 +48,28 @@ struct Sim {
             derivs_dense<Mdl, R>(X + (size_t)t * D, p, F + (size_t)t * N * D, c + (size_t)t * D, C + (size_t)t * D * D);
         }
     }
+    static void riccati(const R* xu, const R* p, R* V, R* v, R* K, R* k) {
+        constexpr int N = Mdl::N, NS = Mdl::NS, NO = Mdl::NO, M = Mdl::M;
+        ValueFn<Mdl, R> vf;
+        vf.clear();
+        for (int i = 0; i < NS; ++i) {
+            vf.vs[i] = v[i];
+            for (int j = i; j < NS; ++j) vf.Vss[i][j] = V[i * N + j];
+        }
+        for (int y = 0; y < NO; ++y) { vf.vyy[y] = V[(NS + y) * N + NS + y]; vf.vy[y] = v[NS + y]; }
+        R Kt[M][NS], kt[M];
+        riccati_step<Mdl, R>(xu, p, vf, Kt, kt);
+        for (int a = 0; a < M; ++a) {
+            for (int j = 0; j < N; ++j) K[a * N + j] = j < NS ? Kt[a][j] : R(-0.0);
+            k[a] = kt[a];
+        }
+        for (int i = 0; i < N * N; ++i) V[i] = R(0);
+        for (int i = 0; i < NS; ++i) {
+            v[i] = vf.vs[i];
+            for (int j = 0; j < NS; ++j) V[i * N + j] = vf.V(i, j);
+        }
+        for (int y = 0; y < NO; ++y) { V[(NS + y) * N + NS + y] = vf.vyy[y]; v[NS + y] = vf.vy[y]; }
+    }
     // One lane of solve_kernel, run sequentially: same stage functions, same compact K layout,
     // same accept / stop / carry logic.
     static void solve(const R* x0, const R* u0, const R* params, int stride_t, double lo, double hi, int T,
@@ -147,7 +169,16 @@ struct Sim {
     extern "C" int hs_backward_dense_##SUFFIX(int n, int m, const R* F, const R* c, const R* C, int T, R* K, R* k) {   \
         if (n == 6 && m == 2) backward_dense<6, 2, R>(F, c, C, T, K, k);                                               \
         else if (n == 8 && m == 3) backward_dense<8, 3, R>(F, c, C, T, K, k);                                          \
+        else if (n == 4 && m == 1) backward_dense<4, 1, R>(F, c, C, T, K, k);                                          \
+        else if (n == 5 && m == 1) backward_dense<5, 1, R>(F, c, C, T, K, k);                                          \
+        else if (n == 4 && m == 2) backward_dense<4, 2, R>(F, c, C, T, K, k);                                          \
         else return -2;                                                                                                \
+        return 0;                                                                                                      \
+    }                                                                                                                  \
+    /* one STRUCTURED Riccati step (riccati_step, what the solve kernel runs) from a caller-supplied value function: \
+       V [N][N] dense (block diagonal: state block + diagonal output block), v [N]; both are updated in place */     \
+    extern "C" int hs_riccati_step_##SUFFIX(int model, const R* xu, const R* p, R* V, R* v, R* K, R* k) {             \
+        HS_DISPATCH(model, (Sim<Mdl, R>::riccati(xu, p, V, v, K, k)));                                                 \
         return 0;                                                                                                      \
     }                                                                                                                  \
     extern "C" int hs_solve_##SUFFIX(int model, const R* x0, const R* u0, const R* params, int stride_t, double lo,    \

@@ -189,3 +189,24 @@ def test_branch_free_sincos_accuracy():
     sf, cf = np.zeros_like(xf), np.zeros_like(xf)
     lib().hs_sincos_f32(xf.ctypes.data_as(vp), len(xf), sf.ctypes.data_as(vp), cf.ctypes.data_as(vp))
     assert np.max(np.abs(sf - np.sin(xf.astype(np.float64)))) <= 3e-7 and np.max(np.abs(cf - np.cos(xf.astype(np.float64)))) <= 3e-7
+
+
+@pytest.mark.parametrize("tag,min_stable", [("RoboticArm_T100", 11), ("RoboticArm_T200", 0)])
+def test_robotic_arm_envelope_rule(golden, tag, min_stable):
+    """SURVEY.md section 4.3 per problem on the seeded RoboticArm batches (BASELINE config 3 is RoboticArm, T = 200):
+    see tests/envelope_rule.py for the rule and the fixtures.  The same test runs on the GPU through the C ABI
+    (tests/test_gpu_solve_parity.py::test_robotic_arm_envelope_rule)."""
+    import envelope_rule as er
+    g, e = golden(tag), golden("Envelope_" + tag)
+    env = er.Envelope(g, e)
+    hs = HostSim(str(g["model"]))
+    T = int(g["T"])
+    verdicts = []
+    for b in range(env.B):
+        r = hs.solve(g["batch_x0"][b], g["batch_target"][b], T)
+        assert r["converged"] and np.isfinite(r["J"])
+        verdicts.append(env.judge(b, r["iters"], r["alphas"], r["J"]))
+    s = er.summarise(verdicts)
+    print(tag, s)
+    assert s["trace_stable"] >= min_stable
+    assert s["passed"] == s["problems"], (s, [v for v in verdicts if not v["ok"]])

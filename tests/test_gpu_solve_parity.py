@@ -74,10 +74,10 @@ def test_seeded_batch(golden, tag):
 
 
 @pytest.mark.parametrize("tag", ["RoboticArm_T100", "RoboticArm_T200"])
-def test_robotic_arm_noise_envelope(golden, tag):
-    """RoboticArm is reference-unstable: require the default problem's iteration
-    trace to match, its cost within the reference's own 1e-15-noise spread (x4 head-room), and every
-    batch problem to end at a cost no worse than 1% above the reference's."""
+def test_robotic_arm_default_problem(golden, tag):
+    """RoboticArm is reference-unstable.  T = 100 default: the reference's 6 iterations and accepted
+    steps, cost within 4x the reference's own 1e-15-noise spread; T = 200 default (the reference's own iteration count is
+    5 ... 11 under that noise): an iteration count the reference shows, or a cost inside its spread."""
     g = golden(tag)
     algo = make_algo(str(g["model"]), int(g["T"]))
     res = algo.solve_batch(g["default_x0"][None], g["default_target"][None], trace=True).to_host()
@@ -86,16 +86,31 @@ def test_robotic_arm_noise_envelope(golden, tag):
     iters_seen = set(g["default_noise_iters"].tolist()) | {int(g["default_iters"])}
     assert int(res.iterations[0]) in iters_seen or abs(res.obj_fun_value[0] - Jref) <= 4 * spread * Jref
     if int(g["T"]) == 100:
-        assert int(res.iterations[0]) == int(g["default_iters"])
+        n = int(g["default_iters"])
+        assert int(res.iterations[0]) == n and np.array_equal(res.alpha_trace[0, :n], g["default_alphas"])
         assert abs(res.obj_fun_value[0] - Jref) <= max(4 * spread, 2e-6) * Jref
-    # the seeded batch is chaotic for the reference itself (0/8 noise-stable at T=200): require normal
-    # termination, an improvement over the initial cost, and final costs of the same magnitude
-    bres = algo.solve_batch(g["batch_x0"], g["batch_target"]).to_host()
+
+
+@pytest.mark.parametrize("tag,min_stable", [("RoboticArm_T100", 11), ("RoboticArm_T200", 0)])
+def test_robotic_arm_envelope_rule(golden, tag, min_stable):
+    """SURVEY.md section 4.3, PER PROBLEM, on the seeded RoboticArm batches (BASELINE config 3 is RoboticArm at T = 200):
+    every problem whose reference trace survives 24 rounding-sized perturbations must be reproduced with the same
+    iteration count and accepted steps and a cost within max(1e-9, 2 x the reference's own radius); every other problem
+    must show one of the reference's 25 traces or a cost inside the reference's envelope (tests/envelope_rule.py;
+    fixtures from the unmodified reference: oracle/make_golden_envelope.py)."""
+    import envelope_rule as er
+    g, e = golden(tag), golden("Envelope_" + tag)
+    env = er.Envelope(g, e)
+    algo = make_algo(str(g["model"]), int(g["T"]))
+    res = algo.solve_batch(g["batch_x0"], g["batch_target"], trace=True).to_host()
+    assert np.all(np.isfinite(res.obj_fun_value)) and np.all(res.converged == 1)
     J0 = algo._dev.rollout(g["batch_x0"], g["batch_target"])[1].cpu().numpy()
-    assert np.all(np.isfinite(bres.obj_fun_value)) and np.all(bres.converged == 1)
-    assert np.all(bres.obj_fun_value < J0)
-    ratio = np.median(bres.obj_fun_value / g["batch_J"])
-    assert 0.5 <= ratio <= 2.0
+    assert np.all(res.obj_fun_value < J0)
+    verdicts = [env.judge(b, res.iterations[b], res.alpha_trace[b], res.obj_fun_value[b]) for b in range(env.B)]
+    s = er.summarise(verdicts)
+    print(tag, s)
+    assert s["trace_stable"] >= min_stable
+    assert s["passed"] == s["problems"], (s, [v for v in verdicts if not v["ok"]])
 
 
 def f32_stable_mask(g, tol=1e-4):

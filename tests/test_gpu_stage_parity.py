@@ -118,3 +118,98 @@ def test_float32_stage_accuracy(golden):
     assert rel(X.cpu().numpy()[0], g["default_X_init"]) <= 1e-6
     K, k = dev.backward(g["stage1_X"][None], tgt)
     assert rel(K.cpu().numpy()[0], g["stage1_K"]) <= 1e-3
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Pivoted LU and teacher-forced Riccati steps through the C ABI.  Same inputs and bounds as the
+# host-build tests in tests/test_riccati_teacher_forced.py; reference: ilqr_wrapper.py:240-255.
+
+def dense_backward(n, m, F, c, C):
+    """crl_backward_dense (the reference's backward_pass(C, c, F) signature) for any compiled (n, m); numpy in / out."""
+    import ctypes
+    from curiousrl_b200 import _native
+    lib = _native.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    Ft = torch.as_tensor(np.ascontiguousarray(F, dtype=np.float64)).to(dev)
+    B, T = Ft.shape[0], Ft.shape[1]
+    ct = torch.as_tensor(np.ascontiguousarray(c, dtype=np.float64)).to(dev)
+    Ct = torch.as_tensor(np.ascontiguousarray(C, dtype=np.float64)).to(dev)
+    K = torch.empty((B, T, m, n), dtype=torch.float64, device=dev)
+    k = torch.empty((B, T, m), dtype=torch.float64, device=dev)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    _native.check(lib.crl_backward_dense(n, m, 0, B, T, p(Ft), p(ct), p(Ct), p(K), p(k),
+                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "crl_backward_dense")
+    return K.cpu().numpy(), k.cpu().numpy()
+
+
+@pytest.mark.parametrize("n,m", [(6, 2), (8, 3), (4, 1), (5, 1), (4, 2)])
+def test_pivoted_lu_against_numpy(n, m):
+    """crl_backward_dense with T = 1 is K = -solve(Quu, Qux), k = -solve(Quu, qu) for a caller-chosen Quu: non-symmetric,
+    indefinite, negative definite, with row exchanges (one and two), zero / tied / tiny pivots, cond up to 1e10."""
+    import riccati_cases as rc
+    rng = np.random.default_rng(100 * n + m)
+    names, Fs, cs, Cs, Ks, ks, conds = [], [], [], [], [], [], []
+    for rep in range(20):
+        for name, A in rc.lu_blocks(m, rng).items():
+            F, c, C, Kref, kref = rc.lu_problem(n, m, A, rng)
+            names.append(name); Fs.append(F); cs.append(c); Cs.append(C); Ks.append(Kref); ks.append(kref)
+            conds.append(np.linalg.cond(A))
+    K, k = dense_backward(n, m, np.stack(Fs), np.stack(cs), np.stack(Cs))
+    for i, name in enumerate(names):
+        tol = 4 * conds[i] * rc.EPS
+        assert np.abs(K[i, 0] - Ks[i]).max() <= tol * np.abs(Ks[i]).max(), (name, conds[i])
+        assert np.abs(k[i, 0] - ks[i]).max() <= tol * np.abs(ks[i]).max(), (name, conds[i])
+
+
+@pytest.mark.parametrize("it", [0, 1, 5])
+def test_dense_riccati_teacher_forced_robotic_arm_t200(golden, it):
+    """RoboticArm T = 200 (BASELINE config 3): every step of the reference's backward pass from the reference's own F, c, C
+    and value function - 28 / 9 / 15 of the 200 steps have a non-PD Quu, 29 / 43 / 55 exchange rows - within
+    4 cond(Quu) eps; and windows of 4 and 8 consecutive steps wherever the recursion's own amplification keeps the bound
+    below 1e-8."""
+    import riccati_cases as rc
+    g = golden("RoboticArm_T200")
+    pre = "stage%d_" % it
+    F, c, C, K, k = (g[pre + s] for s in ("F", "c", "C", "K", "k"))
+    ref = rc.reference_value_functions(F, c, C, 6, 2)
+    assert np.array_equal(ref["K"], K) and np.array_equal(ref["k"], k)
+    assert (ref["lam_min"] < 0).sum() >= 9 and ref["swap"].sum() >= 29
+    starts, Fw, cw, Cw = rc.teacher_forced_windows(F, c, C, ref["V"], ref["v"], 1)
+    Kd, kd = dense_backward(6, 2, Fw, cw, Cw)
+    for b, t in enumerate(starts):
+        tol = 4 * ref["cond"][t] * rc.EPS
+        assert np.abs(Kd[b, 0] - K[t]).max() <= tol * ref["K_scale"][t], (t, ref["lam_min"][t], ref["swap"][t])
+        assert np.abs(kd[b, 0] - k[t]).max() <= tol * ref["k_scale"][t], t
+    Vn = np.abs(ref["V"]).reshape(len(ref["V"]), -1).max(axis=1)
+    for L in (4, 8):
+        starts, Fw, cw, Cw = rc.teacher_forced_windows(F, c, C, ref["V"], ref["v"], L)
+        Kd, kd = dense_backward(6, 2, Fw, cw, Cw)
+        checked, checked_bad = 0, 0
+        for b, t0 in enumerate(starts):
+            win = slice(t0, t0 + L)
+            growth = max(1.0, Vn[t0 + 1:t0 + L + 1].max() / max(Vn[t0 + 1:t0 + L + 1].min(), 1e-300))
+            tol = 64.0 * L * ref["cond"][win].max() * min(growth, 1e30) * rc.EPS
+            if tol > 1e-8:
+                continue
+            assert rc.rel_rows(Kd[b, :L], K[t0:t0 + L]).max() <= tol, (L, t0)
+            checked += 1
+            checked_bad += int((ref["lam_min"][win] < 0).any())
+        assert checked >= 100 and checked_bad > 0
+
+
+@pytest.mark.parametrize("tag", ["RoboticArm_T200", "RoboticArm_T100", "ThreeLink_T100"])
+def test_fused_backward_equals_host_build(golden, tag):
+    """The structured Riccati pass (crl_backward: F, c, C recomputed from X, what the solve kernel runs) on the GPU is the
+    SAME arithmetic as the g++ build of the same headers, so the host build's teacher-forced parity at every step
+    (tests/test_riccati_teacher_forced.py::test_structured_step_teacher_forced, non-PD steps included) carries over:
+    gains bit-equal on the reference's stage trajectories, also where the recursion has blown up (|V| ~ 1e21)."""
+    from hostsim import HostSim
+    g = golden(tag)
+    dev = device_model(g)
+    hs = HostSim(str(g["model"]))
+    tgt = g["default_target"]
+    for it in g["stage_iters"]:
+        X = g["stage%d_X" % it]
+        K, k = dev.backward(X[None], tgt)
+        Kh, kh = hs.backward(X, tgt)
+        assert np.array_equal(K.cpu().numpy()[0], Kh) and np.array_equal(k.cpu().numpy()[0], kh)

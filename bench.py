@@ -14,9 +14,16 @@ solver's own per-trajectory iteration counts.
 value   device-timed throughput, inputs resident in HBM (CUDA events on the launch stream).
 e2e     same metric through the public API (`BasiciLQR.solve_batch`) from pinned HOST buffers:
         H2D of initial states/targets and D2H of costs/iteration counts/flags/trajectories inside
-        the timed region.
+        the timed region (the trajectories are written by the kernel straight into pinned host
+        memory as they finish, `trajectory_to_host=True`, so that copy overlaps the solve).
 roofline  achieved algorithmic HBM bytes/s of the solve kernel vs the measured copy bandwidth.
-cpu_baseline  the CPU oracle port (numba substrate, as the reference) on the host cores, N=1 only.
+also    the other BASELINE configs measured in the SAME run (device-timed, fewer steps): ThreeLink
+        1,048,576 trajectories on one GPU to convergence (north_star's configuration), the headline batch
+        in fixed-work mode (is_check_stop=False, max_iter=20), RoboticArm 262,144 x T=200 FP64
+        (config 3); under --gpus 8 the config-4 shard size (131,072 per GPU).  `--no-also` skips them.
+cpu_baseline / --impl reference   the UNMODIFIED reference through oracle/ref_runner.py when it is installed
+        on the box (baseline/_ref/, oracle/vendor_reference.sh; "kind": "reference", as shipped and numerics
+        only), else the bit-checked port oracle/ilqr_numpy.py ("kind": "port"); host cores, N=1 / rank 0 only.
 """
 from __future__ import annotations
 
@@ -58,6 +65,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="trajectories per core for the CPU baseline (0 = auto)")
     ap.add_argument("--grid-blocks", type=int, default=0)
+    ap.add_argument("--no-also", action="store_true", help="skip the `also` block (the other BASELINE configs)")
+    ap.add_argument("--cpu-kind", default="auto", choices=["auto", "reference", "port"],
+                    help="CPU arm: the unmodified reference (needs baseline/_ref/), the oracle port, or whichever is there")
     return ap.parse_args()
 
 
@@ -207,29 +217,82 @@ def _ready(_):
     return 0
 
 
+# ----------------------------------------------------------------------------- CPU arm: reference or port
+def cpu_arm(args):
+    """-> (kind, pool-like object with .cores / .sample(per_core, seed, as_shipped) / .close())."""
+    from oracle import ref_shim                            # CPU baseline / reference arm only (see module docstring)
+    want = args.cpu_kind
+    if want != "port" and ref_shim.vendored():
+        from oracle import ref_runner
+
+        class Ref:
+            kind = "reference"
+
+            def __init__(self):
+                self.pool = ref_runner.ReferencePool(ref_shim.VENDORED_ROOT, args.model, args.horizon, solver=args.solver)
+                self.cores = self.pool.cores
+
+            def sample(self, per_core, seed, as_shipped=True):
+                x0, tgt = bench_inputs(args.model, per_core * self.cores, seed, args.horizon)
+                return self.pool.run(x0, tgt, as_shipped)
+
+            def close(self):
+                self.pool.close()
+
+        return Ref()
+    if want == "reference":
+        raise SystemExit("bench.py: --cpu-kind reference needs baseline/_ref/ (bash oracle/vendor_reference.sh)")
+
+    class Port:
+        kind = "port"
+
+        def __init__(self):
+            self.pool = CpuReference(args.model, args.horizon, solver=args.solver)
+            self.cores = self.pool.cores
+
+        def sample(self, per_core, seed, as_shipped=True):
+            return self.pool.run(per_core, seed)
+
+        def close(self):
+            self.pool.close()
+
+    return Port()
+
+
+def cpu_description(arm, per_core, iters, wall):
+    what = ("the UNMODIFIED reference (baseline/_ref, through the import shim oracle/ref_shim.py), BasiciLQR.solve() as shipped "
+            "- including its per-iteration json.dumps of the trajectory (basic_ilqr.py:93) -" if arm.kind == "reference" else
+            "CPU oracle port (oracle/ilqr_numpy.py, bit-checked against the reference) on the reference's numba+BLAS substrate,")
+    return ("first %d trajectories of the same seeded batch (%d per core; %d traj-iters in %.1f s), %s one single-threaded "
+            "worker process per core, numba JIT warm-up excluded" % (per_core * arm.cores, per_core, iters, wall, what))
+
+
 # ----------------------------------------------------------------------------- reference arm
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     per_core = args.cpu_sample or 64
-    ref = CpuReference(args.model, args.horizon, solver=args.solver)
+    arm = cpu_arm(args)
     iters_tot, wall_tot = 0, 0.0
     for step in range(args.warmup + args.steps):
-        iters, wall = ref.run(per_core, seed=1234)
+        iters, wall = arm.sample(per_core, seed=1234)
         if step >= args.warmup:
             iters_tot += iters
             wall_tot += wall
-    ref.close()
     value = iters_tot / wall_tot
-    sample = ("each step = the first %d trajectories of the seeded batch (%d per core), CPU oracle port on the numba+BLAS "
-              "substrate of the reference, one single-threaded worker per core, JIT warm-up excluded" % (
-                  per_core * ref.cores, per_core))
+    base = {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+            "sample": "each step = " + cpu_description(arm, per_core, iters_tot // max(1, args.steps), wall_tot / max(1, args.steps))}
+    if arm.kind == "reference":                       # SURVEY 8(d): both flavours
+        it2, w2 = arm.sample(per_core, seed=1234, as_shipped=False)
+        base["numerics_only_value"] = it2 / w2
+        base["note"] = "value = as shipped; numerics_only_value = the same with logger.save_to_json replaced by a no-op"
+    arm.close()
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall_tot / max(1, args.steps), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": "port", "sample": sample},
+            "cpu_baseline": base,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -338,11 +401,16 @@ def run_b200(args):
     it_h = torch.empty(B, dtype=torch.int32).pin_memory()
     cv_h = torch.empty(B, dtype=torch.uint8).pin_memory()
     X_h = torch.empty((B, T, dm.d), dtype=dm.dtype).pin_memory()
+    out_h = None
+    if args.solver == "basic":      # the kernel writes finished trajectories straight into X_h (mapped pinned host memory)
+        from curiousrl_b200.algorithm.ilqr_solver.device import BatchResult
+        out_h = BatchResult(X_h, torch.empty(B, dtype=torch.float64, device=dev), torch.empty(B, dtype=torch.int32, device=dev),
+                            torch.empty(B, dtype=torch.uint8, device=dev))
 
     def step_e2e():
         tgt_in = None if tgt_pin is None else tgt_pin.to(dev, non_blocking=True)
         if args.solver == "basic":
-            r = algo.solve_batch(x0_pin.to(dev, non_blocking=True), tgt_in, out=out)
+            r = algo.solve_batch(x0_pin.to(dev, non_blocking=True), tgt_in, out=out_h, trajectory_to_host=True)
         else:
             r = algo.solve_batch(x0_pin.to(dev, non_blocking=True), tgt_in)
         if world > 1:
@@ -350,7 +418,8 @@ def run_b200(args):
         J_h.copy_(r.obj_fun_value, non_blocking=True)
         it_h.copy_(r.iterations, non_blocking=True)
         cv_h.copy_(r.converged, non_blocking=True)
-        X_h.copy_(r.trajectory, non_blocking=True)
+        if r.trajectory is not X_h:
+            X_h.copy_(r.trajectory, non_blocking=True)
         torch.cuda.synchronize()
 
     step_e2e()
@@ -367,6 +436,63 @@ def run_b200(args):
     e2e_value = iters_all / float(e2e_t[0])
     h2d = x0_pin.numel() * x0_pin.element_size() + (0 if tgt_pin is None else tgt_pin.numel() * tgt_pin.element_size())
     d2h = sum(t.numel() * t.element_size() for t in (J_h, it_h, cv_h, X_h))
+
+    # ---- the other BASELINE configs, device-timed in the same run (every rank takes part; max over ranks)
+    also = []
+    if not args.no_also and args.solver == "basic" and args.model == MODEL and args.mode == "converge" and B == 65536 \
+            and args.dtype == "float64":
+        flush = None                                  # free the 512 MB flush buffer
+        peak_also = measured_hbm_peak()[0]
+
+        def measure(name, model, batch, horizon, steps, **solver_kw):
+            """One more workload on this rank's GPU: 1 warm-up + `steps` timed solves, CUDA events, max over ranks."""
+            algo2 = BasiciLQR(max_line_search=MAX_LINE_SEARCH, **solver_kw).init(getattr(models, model)(T=horizon))
+            xh, th = bench_inputs(model, batch, 1234 + rank, horizon)
+            xd, td = algo2._dev.real(xh), algo2._dev.real(th)
+            o2 = algo2.solve_batch(xd, td)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            tot = 0.0
+            for _ in range(steps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                o2 = algo2.solve_batch(xd, td, out=o2)
+                if world > 1:
+                    gather_results(o2.obj_fun_value, o2.iterations, o2.converged, batch * world)
+                e1.record()
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+            it_loc = float(o2.iterations.sum().item())
+            st = torch.tensor([tot / steps, it_loc], dtype=torch.float64, device=dev)
+            if world > 1:
+                mx, sm_ = st.clone(), st.clone()
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+                dist.all_reduce(sm_, op=dist.ReduceOp.SUM)
+                ms2, it_all = float(mx[0]), float(sm_[1])
+            else:
+                ms2, it_all = float(st[0]), it_loc
+            d2 = algo2._dev
+            bpi2 = bytes_per_traj_iter(d2.n, d2.m, horizon, 8)
+            rec = {"workload": name, "model": model, "batch_per_gpu": batch, "horizon": horizon, "dtype": "f64",
+                   "steps": steps, "warmup": 1, "ms_per_step": ms2, "traj_iters_per_step": it_all,
+                   "value": it_all / (ms2 * 1e-3), "unit": UNIT,
+                   "frac": (it_loc * bpi2) / (ms2 * 1e-3) / 1e9 / peak_also,
+                   "algorithmic_bytes_per_traj_iter": bpi2, "timing": "CUDA events on the launch stream, max over ranks"}
+            del algo2, xd, td, o2
+            torch.cuda.empty_cache()
+            return rec
+
+        also.append(measure("fixed work: ThreeLink 65,536 per GPU, T=100, FP64, is_check_stop=False, max_iter=20 (SURVEY 8(d))",
+                            MODEL, 65536, 100, 3, is_check_stop=False, max_iter=20))
+        if world == 1:
+            also.append(measure("north_star configuration: ThreeLink 1,048,576 trajectories on ONE GPU, T=100, FP64, to convergence",
+                                MODEL, 1048576, 100, 2))
+            also.append(measure("BASELINE config 3: RoboticArmTracking 262,144, T=200, FP64, to convergence",
+                                "RoboticArmTracking", 262144, 200, 2))
+        else:
+            also.append(measure("BASELINE config 4 shard size: ThreeLink 131,072 per GPU (x %d GPUs = %d), T=100, FP64, to "
+                                "convergence, terminal gather included" % (world, 131072 * world), MODEL, 131072, 100, 2))
 
     if rank != 0:
         if world > 1:
@@ -397,16 +523,20 @@ def run_b200(args):
     if tr is not None:
         line["roofline"]["traffic"] = tr["dram_bytes"]
         line["roofline"]["traffic_source"] = tr.get("source")
+    if not args.no_also and args.solver == "basic" and args.model == MODEL and args.mode == "converge" and args.batch == 65536 \
+            and args.dtype == "float64":
+        line["also"] = also
     if world == 1 and not args.no_cpu_baseline:
         per_core = args.cpu_sample or 256           # the first 256 x cores trajectories (~15-20 s)
         try:
-            ref = CpuReference(args.model, T, solver=args.solver)
-            iters, wall = ref.run(per_core, seed=1234)
-            ref.close()
-            line["cpu_baseline"] = {"value": iters / wall, "unit": UNIT, "cores": ref.cores, "kind": "port",
-                                    "sample": "first %d trajectories of the same seeded batch (%d per core; %d traj-iters in "
-                                              "%.1f s), CPU oracle port on the reference's numba+BLAS substrate, JIT warm-up "
-                                              "excluded" % (per_core * ref.cores, per_core, iters, wall)}
+            arm = cpu_arm(args)
+            iters, wall = arm.sample(per_core, seed=1234)
+            line["cpu_baseline"] = {"value": iters / wall, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+                                    "sample": cpu_description(arm, per_core, iters, wall)}
+            if arm.kind == "reference":
+                it2, w2 = arm.sample(max(32, per_core // 4), seed=1234, as_shipped=False)
+                line["cpu_baseline"]["numerics_only_value"] = it2 / w2
+            arm.close()
         except Exception as exc:      # the baseline is reporting only; never lose the GPU line
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                     "sample": "failed: %r" % (exc,)}

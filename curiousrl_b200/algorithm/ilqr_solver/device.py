@@ -68,6 +68,7 @@ class DeviceModel:
         if self._bounds is not None and not self.generic:
             raise ValueError("per-component bounds are for the generated models")
         self._workspace = None
+        self._workspaces = {}      # stream handle -> workspace tensor
         self.launches = 0          # kernels enqueued through this object (bench accounting)
 
     # ------------------------------------------------------------------ tensor plumbing
@@ -209,9 +210,34 @@ class DeviceModel:
         need = self.lib.crl_solve_workspace_bytes(prob, ctypes.byref(opts))
         if need == 0:
             raise RuntimeError("curiousrl_b200: cannot size the solver workspace (no CUDA device?)")
-        if self._workspace is None or self._workspace.numel() < need:
-            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)   # caching allocator: 512 B aligned
-        return self._workspace
+        # one workspace per stream: the control block and the tiles belong to the solve that is in flight, and two
+        # solves enqueued on different streams from one solver object would otherwise share them
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        ws = self._workspaces.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=self.device)   # caching allocator: 512 B aligned
+            self._workspaces[key] = ws
+        self._workspace = ws                                                  # the most recent one (phase timers, tools)
+        return ws
+
+    def _check_out(self, out: BatchResult, B: int, max_iter: int):
+        """A caller-supplied result object is written by raw pointer: refuse anything the kernel would overrun."""
+        def need(name, t, shape, dtype, host_ok=False):
+            if t is None:
+                return
+            where_ok = (t.device == self.device) or (host_ok and t.device.type == "cpu" and t.is_pinned())
+            if tuple(t.shape) != tuple(shape) or t.dtype != dtype or not t.is_contiguous() or not where_ok:
+                raise ValueError("out.%s must be a contiguous %s tensor of shape %s on %s%s (got %s %s on %s)" % (
+                    name, dtype, tuple(shape), self.device, " or in pinned host memory" if host_ok else "",
+                    t.dtype, tuple(t.shape), t.device))
+        need("trajectory", out.trajectory, (B, self.T, self.d), self.dtype, host_ok=True)
+        need("obj_fun_value", out.obj_fun_value, (B,), torch.float64)
+        need("iterations", out.iterations, (B,), torch.int32)
+        need("converged", out.converged, (B,), torch.uint8)
+        need("obj_fun_trace", out.obj_fun_trace, (B, max_iter), torch.float64)
+        need("alpha_trace", out.alpha_trace, (B, max_iter), torch.int8)
+        if out.obj_fun_value is None or out.iterations is None or out.converged is None:
+            raise ValueError("out.obj_fun_value, out.iterations and out.converged are required")
 
     def solve(self, opts: _native.SolverOpts, x0, params, u0=None, J_init=None, return_trajectory=True,
               trace=False, out: Optional[BatchResult] = None) -> BatchResult:
@@ -226,6 +252,8 @@ class DeviceModel:
             if J_init.numel() == 1:
                 J_init = J_init.expand(B)
             J_init = J_init.contiguous()
+        if out is not None:
+            self._check_out(out, B, opts.max_iter)
         if out is None:
             out = BatchResult(self.empty(B, self.T, self.d) if return_trajectory else None,
                               self.empty(B, dtype=torch.float64), self.empty(B, dtype=torch.int32),

@@ -113,9 +113,32 @@ class LogBarrieriLQR(iLQRWrapper):
         self._obj_fun = iLQRObjectiveFunction(self._dev, add_param, self)
         self._real_obj_fun = iLQRObjectiveFunction(self._real_dev, None, _RealCostOwner(self))
         self._t_stale = None
-        if self._verify and not self._generic:         # generated models: the plain model is verified by BasiciLQR.init; the
-            self._verify_against(scenario)             # barrier terms come from the same generator (tests pin them)
+        if self._verify:
+            # the device model is chosen by the scenario's NAME: check the scenario's own sympy definition against it, so
+            # that a subclass / edited scenario of the same name cannot silently run the compiled default expressions
+            if self._generic:
+                self._verify_generic(scenario)
+            self._verify_against(scenario)
         return self
+
+    def _verify_generic(self, scenario):
+        """Generated device model under the barrier cost: dynamics (one closed-loop step with zero gains) against the
+        scenario's sympy f.  The cost + barrier terms are checked by _verify_against."""
+        import sympy as sp
+        dev, rng = self._real_dev, np.random.default_rng(2468)
+        xu = scenario.x_u_var
+        f_expr = scenario.dynamic_function
+        f = sp.lambdify([xu], f_expr.tolist() if hasattr(f_expr, "tolist") else f_expr, "math")
+        constr = np.asarray(scenario.constr, dtype=np.float64)
+        lo, hi = np.maximum(constr[:, 0], -0.5), np.minimum(constr[:, 1], 0.5)
+        prm = _RealCostOwner(self)._params_for(1)
+        if dev.T > 1:
+            for _ in range(3):
+                X = rng.uniform(lo, hi, (1, dev.T, dev.d))
+                Xn, _ = dev.update_traj(X, np.zeros((1, dev.T, dev.m, dev.n)), np.zeros((1, dev.T, dev.m)), 0.0, prm)
+                x1 = np.clip(np.asarray(f(X[0, 0]), dtype=np.float64), constr[:dev.n, 0], constr[:dev.n, 1])
+                if not np.allclose(Xn.cpu().numpy()[0, 1, :dev.n], x1, rtol=1e-9, atol=1e-9):
+                    raise Exception('Scenario "%s": dynamic_function differs from the device model' % scenario.name)
 
     def _verify_against(self, scenario):
         """The barrier cost of the device model against the scenario's own symbolic cost + barrier terms."""
@@ -128,6 +151,22 @@ class LogBarrieriLQR(iLQRWrapper):
                 expr = expr + (-1 / t_var) * sp.log(-(c[0] - xu[i]))
             if not np.isinf(c[1]):
                 expr = expr + (-1 / t_var) * sp.log(-(xu[i] - c[1]))
+        if self._generic:
+            # the scenario's own (time-varying) parameter rows + t, states and actions inside the box (the barrier of a
+            # generated model sits on the state bounds too)
+            pv = tuple(scenario.add_param_var) if scenario.add_param_var is not None else ()
+            l = sp.lambdify([xu, (*pv, t_var)], expr, "math")
+            constr = np.asarray(scenario.constr, dtype=np.float64)
+            lo, hi = np.maximum(constr[:, 0], -0.5), np.minimum(constr[:, 1], 0.5)
+            P = self._params_for(1)
+            Ph = P.cpu().numpy()[0]
+            for _ in range(3):
+                X = rng.uniform(lo + 0.05 * (hi - lo), hi - 0.05 * (hi - lo), (1, dev.T, dev.d))
+                J = float(dev.cost(X, P).item())
+                J_ref = sum(float(l(X[0, t], Ph[t, :len(pv) + 1])) for t in range(dev.T))
+                if not np.isclose(J, J_ref, rtol=1e-9):
+                    raise Exception('Scenario "%s": obj_fun + barrier differs from the device model' % scenario.name)
+            return
         l = sp.lambdify([xu, (*scenario.add_param_var, t_var)], expr, "math")
         for _ in range(3):
             X = rng.uniform(-2.0, 2.0, (1, dev.T, dev.d))

@@ -183,6 +183,16 @@ class iLQRWrapper(AlgoWrapper):
     def get_obj_add_param(self):
         return self._obj_fun._add_param
 
+    def _host_trajectory(self, B):
+        """Pinned host buffer [B, T, n+m] for `solve_batch(trajectory_to_host=True)` (cached: pinning 0.6 GB takes longer
+        than the solve)."""
+        dev = self._dev
+        buf = getattr(self, "_host_traj_buf", None)
+        if buf is None or tuple(buf.shape) != (B, dev.T, dev.d) or buf.dtype != dev.dtype:
+            buf = torch.empty((B, dev.T, dev.d), dtype=dev.dtype, pin_memory=True)
+            self._host_traj_buf = buf
+        return buf
+
     # -- batched re-solve (receding horizon) ---------------------------------------------------
     def resolve_batch(self, previous, at_step, add_param=None, warm_start=False, **solve_kwargs):
         """Batched form of the Examples' re-solve (Example/ThreeLinkPlanarManipulatorInteractive.py:18-31: new target,
@@ -357,11 +367,18 @@ class BasiciLQR(iLQRWrapper):
 
     # ------------------------------------------------------------------ batched extension
     def solve_batch(self, init_state, add_param=None, init_action=None, obj_fun_value=None, return_trajectory=True,
-                    trace=False, out: Optional[BatchResult] = None) -> BatchResult:
+                    trace=False, out: Optional[BatchResult] = None, trajectory_to_host=False) -> BatchResult:
         """Solve B independent problems in one persistent kernel.
 
-        init_state [B, n]; add_param [B, p] (constant target per problem), [B, T, p], [T, p] (shared) or
-        None (the scenario's); init_action None (the scenario's), [T, m] or [B, T, m]; obj_fun_value: initial
+        trajectory_to_host=True: the kernel writes every finished trajectory straight into PINNED HOST memory (mapped
+        into the device's address space; 256-byte coalesced stores over PCIe) while the other trajectories are still
+        being iterated - the device-to-host copy of the [B, T, n+m] result overlaps the solve instead of following it.
+        `result.trajectory` is then a pinned CPU tensor, complete once the stream has been synchronised; the buffer
+        is owned by the solver and reused by the next call with the same batch size.
+
+        init_state [B, n]; add_param [B, p] or [B, 1, p] (constant target per problem), [B, T, p], [T, p] or
+        [1, T, p] (one time-varying table shared by the batch; [T, p] is refused when B == T because it cannot be
+        told from [B, p]) or None (the scenario's); init_action None (the scenario's), [T, m] or [B, T, m]; obj_fun_value: initial
         "last cost" (scalar or [B]; default +inf, i.e. `set_obj_fun_value(np.inf)` for every problem).
         NumPy or torch inputs; outputs are torch tensors on the solver's device.
         """
@@ -372,11 +389,26 @@ class BasiciLQR(iLQRWrapper):
             prm = self._params_for(B)
         else:
             prm = dev.real(add_param)
-            if prm.dim() == 2 and tuple(prm.shape) == (dev.T, dev.p) and B != dev.T:
+            if prm.dim() == 2 and tuple(prm.shape) == (dev.T, dev.p):
+                if B == dev.T:
+                    raise ValueError("add_param of shape [%d, %d] is ambiguous when the batch size equals the horizon: pass "
+                                     "[1, T, p] for one time-varying table shared by the batch or [B, 1, p] / [B, T, p] for "
+                                     "per-problem parameters" % (dev.T, dev.p))
                 prm = prm.reshape(1, dev.T, dev.p)
+            elif prm.dim() == 3 and tuple(prm.shape) == (B, 1, dev.p):
+                prm = prm.reshape(B, dev.p)                       # per-problem constants, spelled unambiguously
         u0 = self._dynamic_model._init_action if init_action is None else init_action
         if isinstance(u0, np.ndarray) and not u0.any():
             u0 = None                      # zeros: let the kernel skip the loads
+        if trajectory_to_host and return_trajectory:
+            if out is None:
+                out = BatchResult(None, dev.empty(B, dtype=torch.float64), dev.empty(B, dtype=torch.int32),
+                                  dev.empty(B, dtype=torch.uint8))
+                if trace:
+                    out.obj_fun_trace = torch.full((B, self._max_iter), float("nan"), dtype=torch.float64, device=dev.device)
+                    out.alpha_trace = torch.full((B, self._max_iter), -2, dtype=torch.int8, device=dev.device)
+            if out.trajectory is None or out.trajectory.device.type != "cpu":
+                out.trajectory = self._host_trajectory(B)
         res = dev.solve(self._opts(self._max_iter, self._is_check_stop), x0, prm, u0=u0,
                         J_init=obj_fun_value,
                         return_trajectory=return_trajectory, trace=trace, out=out)

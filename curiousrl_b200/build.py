@@ -38,46 +38,98 @@ def find_nvcc():
     return cand if cand and os.path.exists(cand) else None
 
 
+HASH_PATH = LIB_PATH + ".srchash"                  # digest of the sources + flags the library was built from
+
+
+def source_digest() -> str:
+    """SHA-256 over the translation units, their headers and the compiler flags."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for p in SOURCES + HEADERS:
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def is_stale():
+    """True if the library is missing or was built from other sources.  Decided by CONTENT (the digest the build wrote
+    next to the library): `git checkout` and the snapshot that ships the tree to a GPU box reset modification times, which
+    made every rank of a torchrun job rebuild a perfectly good library at once.  Without a digest file: by mtime."""
     if not os.path.exists(LIB_PATH):
         return True
+    if os.path.exists(HASH_PATH):
+        with open(HASH_PATH) as f:
+            return f.read().strip() != source_digest()
     built = os.path.getmtime(LIB_PATH)
     return any(os.path.getmtime(p) > built for p in SOURCES + HEADERS if os.path.exists(p))
 
 
+def _unit_digest(src) -> str:
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for p in [src, HEADERS[-1]] + [os.path.join(CSRC, x) for x in UNIT_HEADERS[os.path.basename(src)]]:
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def _unit_stale(src, obj):
-    if not os.path.exists(obj):
+    if not os.path.exists(obj) or not os.path.exists(obj + ".srchash"):
         return True
-    built = os.path.getmtime(obj)
-    deps = [src, HEADERS[-1]] + [os.path.join(CSRC, h) for h in UNIT_HEADERS[os.path.basename(src)]]
-    return any(os.path.getmtime(p) > built for p in deps if os.path.exists(p))
+    with open(obj + ".srchash") as f:
+        return f.read().strip() != _unit_digest(src)
+
+
+def _run(cmd, verbose):
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose:
+        sys.stderr.write(proc.stderr)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr[-4000:]))
 
 
 def build_native(force: bool = False, verbose: bool = False) -> str:
-    """Compile the CUDA library if missing or older than its sources; return its path.  Every translation unit is
-    compiled to its own object (only the changed ones are recompiled) and the objects are linked into the library."""
+    """Compile the CUDA library if missing or built from other sources; return its path.  Every translation unit is
+    compiled to its own object (only the changed ones are recompiled) and the objects are linked into the library.
+
+    Safe under concurrent callers (one process per GPU under torchrun): the whole build holds an exclusive lock, every
+    output is written to a temporary name and renamed into place, and staleness is re-checked once the lock is held, so
+    the ranks that waited find the finished library and never load a half-written one."""
     if not force and not is_stale():
         return LIB_PATH
     nvcc = find_nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found and %s is missing or stale: the CUDA library cannot be built" % LIB_PATH)
+    import fcntl
     os.makedirs(OBJ_DIR, exist_ok=True)
-    objs = []
-    for src in SOURCES:
-        obj = os.path.join(OBJ_DIR, os.path.splitext(os.path.basename(src))[0] + ".o")
-        objs.append(obj)
-        if not force and not _unit_stale(src, obj):
-            continue
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
-        proc = subprocess.run(cmd, capture_output=True, text=True)
-        if verbose:
-            sys.stderr.write(proc.stderr)
-        if proc.returncode != 0:
-            raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr[-4000:]))
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH] + objs
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc link failed:\n%s\n%s" % (" ".join(cmd), proc.stderr[-4000:]))
+    with open(os.path.join(OBJ_DIR, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():          # another process built it while this one waited for the lock
+                return LIB_PATH
+            tag = ".tmp%d" % os.getpid()
+            objs = []
+            for src in SOURCES:
+                obj = os.path.join(OBJ_DIR, os.path.splitext(os.path.basename(src))[0] + ".o")
+                objs.append(obj)
+                if not force and not _unit_stale(src, obj):
+                    continue
+                _run([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj + tag, src], verbose)
+                os.replace(obj + tag, obj)
+                with open(obj + ".srchash" + tag, "w") as f:
+                    f.write(_unit_digest(src))
+                os.replace(obj + ".srchash" + tag, obj + ".srchash")
+            _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH + tag]
+                 + objs, verbose)
+            if os.path.exists(HASH_PATH):
+                os.remove(HASH_PATH)                    # never a new library under an old digest
+            os.replace(LIB_PATH + tag, LIB_PATH)
+            with open(HASH_PATH + tag, "w") as f:
+                f.write(source_digest())
+            os.replace(HASH_PATH + tag, HASH_PATH)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 

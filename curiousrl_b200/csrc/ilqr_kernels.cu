@@ -1552,6 +1552,20 @@ template <class R> struct SolveCfg;
 template <> struct SolveCfg<double> { static constexpr int kDefault = 12; };
 template <> struct SolveCfg<float> { static constexpr int kDefault = 12; };
 
+// A requested grid (opts->grid_blocks) is honoured up to the number of CTAs the device can hold at once.
+static int clamp_grid(int requested, int resident) { return requested > 0 && requested < resident ? requested : resident; }
+
+// Persistent kernels whose CTAs wait for each other (straggler hand-over) are launched cooperatively: the runtime
+// then guarantees that all CTAs are resident together - an oversized grid fails loudly (cudaErrorCooperativeLaunchTooLarge)
+// and a launch that finds part of the device busy with another kernel waits instead of starting a partial grid that
+// would spin for CTAs that can never be scheduled.
+template <class Args>
+static cudaError_t launch_resident(const void* kernel, int grid_blocks, int threads, int smem, cudaStream_t s, const Args& a) {
+    Args copy = a;
+    void* params[] = {&copy};
+    return cudaLaunchCooperativeKernel(kernel, dim3((unsigned)grid_blocks), dim3((unsigned)threads), params, (size_t)smem, s);
+}
+
 template <class Mdl, class R, int WARPS, int MINB, bool SYNC>
 struct SolveVariant {
     static constexpr int kWarps = WARPS;
@@ -1561,7 +1575,6 @@ struct SolveVariant {
         if (cudaFuncSetAttribute(solve_kernel<Mdl, R, WARPS, MINB, SYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  kSmem) != cudaSuccess)
             return -1;
-        if (requested > 0) return requested;
         int dev = 0, sms = 0, per_sm = 0;
         if (cudaGetDevice(&dev) != cudaSuccess) return -1;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
@@ -1569,10 +1582,12 @@ struct SolveVariant {
                                                           kSmem) != cudaSuccess)
             return -1;
         if (per_sm < 1) per_sm = 1;
-        return sms * per_sm;
+        // the tail's finishers wait for every CTA of the grid to report: the grid must be co-resident, so a requested
+        // size is clamped to what fits the device (and the launch below is cooperative, which enforces it)
+        return clamp_grid(requested, sms * per_sm);
     }
-    static void launch(int grid_blocks, cudaStream_t s, const SolveArgs<R>& a) {
-        solve_kernel<Mdl, R, WARPS, MINB, SYNC><<<grid_blocks, WARPS * 32, kSmem, s>>>(a);
+    static cudaError_t launch(int grid_blocks, cudaStream_t s, const SolveArgs<R>& a) {
+        return launch_resident((const void*)solve_kernel<Mdl, R, WARPS, MINB, SYNC>, grid_blocks, WARPS * 32, kSmem, s, a);
     }
 };
 
@@ -1586,7 +1601,6 @@ struct CoopVariant {
         if (cudaFuncSetAttribute(coop_solve_kernel<Mdl, R, WARPS, MINB, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  kSmem) != cudaSuccess)
             return -1;
-        if (requested > 0) return requested;
         int dev = 0, sms = 0, per_sm = 0;
         if (cudaGetDevice(&dev) != cudaSuccess) return -1;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
@@ -1594,10 +1608,10 @@ struct CoopVariant {
                                                           kSmem) != cudaSuccess)
             return -1;
         if (per_sm < 1) per_sm = 1;
-        return sms * per_sm;
+        return clamp_grid(requested, sms * per_sm);
     }
-    static void launch(int grid_blocks, cudaStream_t s, const SolveArgs<R>& a) {
-        coop_solve_kernel<Mdl, R, WARPS, MINB, NT><<<grid_blocks, WARPS * 32, kSmem, s>>>(a);
+    static cudaError_t launch(int grid_blocks, cudaStream_t s, const SolveArgs<R>& a) {
+        return launch_resident((const void*)coop_solve_kernel<Mdl, R, WARPS, MINB, NT>, grid_blocks, WARPS * 32, kSmem, s, a);
     }
 };
 
@@ -1650,9 +1664,11 @@ static int effective_variant(const crl_problem_t* prob, const crl_solver_opts_t*
 }
 
 template <class Mdl, class R>
-static void solve_launch(int variant, int grid, cudaStream_t s, const SolveArgs<R>& a) {
+static cudaError_t solve_launch(int variant, int grid, cudaStream_t s, const SolveArgs<R>& a) {
     const int v = variant > 0 ? variant : SolveCfg<R>::kDefault;
-    CRL_SOLVE_VARIANT(v, V::launch(grid, s, a));
+    cudaError_t e = cudaErrorInvalidValue;
+    CRL_SOLVE_VARIANT(v, e = V::launch(grid, s, a));
+    return e;
 }
 
 }  // namespace crl
@@ -1918,8 +1934,12 @@ static int solve_impl(const crl_problem_t* prob, const crl_solver_opts_t* opts, 
         a.slot_elems = slot_elems;
         a.n_stage = n_stage;
         a.stage_iters = stage_iters;
-        solve_launch<Mdl, R>(effective_variant<Mdl, R>(prob, opts), grid, s, a);
+        e = solve_launch<Mdl, R>(effective_variant<Mdl, R>(prob, opts), grid, s, a);
     });
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return cuda_status(e);
+    }
     return cuda_status(cudaGetLastError());
 }
 

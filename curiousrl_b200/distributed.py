@@ -4,7 +4,7 @@ Trajectories are independent (the reference solves them one at a time through on
 object, Example/*.py:18-31), so rank g simply owns the contiguous slice
 [g*B/G, (g+1)*B/G) and runs the persistent solve kernel on it.  The only communication is
 the terminal gather of per-trajectory cost (8 B), iteration count (4 B) and convergence flag
-(1 B) - 13 B per trajectory; trajectories stay sharded unless asked for.
+(1 B), packed into 16-byte records and sent by ONE all_gather; trajectories stay sharded unless asked for.
 Backend: NCCL over NVLink on GPUs; gloo works for the same code on CPU tensors (tests).
 """
 from __future__ import annotations
@@ -14,6 +14,9 @@ from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist
+
+
+RECORD_BYTES = 16      # one gathered record per trajectory: float64 J | int32 iterations | uint8 converged | 3 pad
 
 
 def shard_range(batch: int, rank: int, world: int) -> Tuple[int, int]:
@@ -52,9 +55,16 @@ def gather_results(obj_fun_value: torch.Tensor, iterations: torch.Tensor, conver
     """Terminal gather: every rank ends up with the whole batch's J / iterations / flags."""
     world = dist.get_world_size(group)
     counts = [shard_range(batch, r, world)[1] - shard_range(batch, r, world)[0] for r in range(world)]
-    J = _all_gather_ragged(obj_fun_value, counts, group)
-    it = _all_gather_ragged(iterations, counts, group)
-    cv = _all_gather_ragged(converged, counts, group)
+    # ONE collective for the three per-trajectory scalars: records of 16 bytes (J: 8, iterations: 4, flag: 1, pad: 3)
+    n = obj_fun_value.shape[0]
+    rec = torch.zeros((n, RECORD_BYTES), dtype=torch.uint8, device=obj_fun_value.device)
+    rec[:, 0:8] = obj_fun_value.to(torch.float64).contiguous().view(torch.uint8).reshape(n, 8)
+    rec[:, 8:12] = iterations.to(torch.int32).contiguous().view(torch.uint8).reshape(n, 4)
+    rec[:, 12] = converged.to(torch.uint8)
+    all_rec = _all_gather_ragged(rec, counts, group)
+    J = all_rec[:, 0:8].contiguous().view(torch.float64).reshape(-1)
+    it = all_rec[:, 8:12].contiguous().view(torch.int32).reshape(-1)
+    cv = all_rec[:, 12].contiguous()
     X = _all_gather_ragged(trajectory, counts, group) if trajectory is not None else None
     return GatheredResult(J, it, cv, X)
 

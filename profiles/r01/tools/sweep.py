@@ -1,0 +1,27 @@
+import os, sys
+sys.path.insert(0, "/root/repo")
+import numpy as np, torch
+from curiousrl_b200 import logger
+from curiousrl_b200.algorithm.ilqr_solver import BasiciLQR
+import curiousrl_b200.scenario.dynamic_model as models
+from curiousrl_b200.utils.synthetic import synthetic_batch
+logger.set_level(45)
+MODEL = "ThreeLinkPlanarManipulator"
+NAMES = ["refill", "backward", "linesearch", "retire", "wait", "gather", "c_backward", "c_linesearch", "c_output"]
+B = int(os.environ.get("B", 65536)); x0, tgt = synthetic_batch(MODEL, B, seed=1234)
+cfgs = [tuple(int(v) for v in c.split(":")) for c in sys.argv[1:]] or [(4, 0), (8, 0), (16, 0)]
+ref = None
+for coop, occ in cfgs:
+    algo = BasiciLQR(max_line_search=10, verify=False, coop_threshold=coop, occupancy=occ).init(getattr(models, MODEL)(T=100))
+    x0d, tgd = algo._dev.real(x0), algo._dev.real(tgt)
+    best = 1e9
+    for _ in range(3):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); res = algo.solve_batch(x0d, tgd, return_trajectory=os.environ.get('RT','1')=='1'); e.record(); torch.cuda.synchronize()
+        best = min(best, s.elapsed_time(e))
+    tm = algo._dev._workspace[:256].view(torch.int64)[8:8 + len(NAMES)].cpu().numpy().astype(np.float64)
+    it = int(res.iterations.sum())
+    chk = (int(res.iterations.sum()), float(res.obj_fun_value.sum()), float(res.trajectory.double().sum()) if res.trajectory is not None else 0.0)
+    if ref is None: ref = chk
+    print("%s B=%d coop=%d variant=%d: %.1f ms, %.2f M traj-iter/s same=%s chk=%r | %s" % (os.environ.get("CURIOUSRL_B200_LIB", "")[-12:], B, coop, occ, best, it / best / 1e3, chk == ref, chk,
+          ", ".join("%s %.1f" % (n, v / 1184 / 1.965e6) for n, v in zip(NAMES, tm))))

@@ -49,6 +49,11 @@ class DeviceModel:
             raise ValueError('the generated device model of "%s" is compiled for float64 only' % model_name)
         if dtype not in _TORCH_DTYPE:
             raise ValueError("dtype must be 'float64' or 'float32'")
+        if dtype == "float32" and model_name == "RoboticArmTracking" and int(T) > 100:
+            # the FP64 reference does not reproduce ITSELF on this scenario beyond T = 100 (1e-15 noise moves its cost by
+            # O(1)); north_star's FP32 bar (1e-4 on the final cost) cannot be stated there, so the mode is not offered
+            raise ValueError('dtype="float32" is not offered for RoboticArmTracking with T > 100: the scenario is chaotic '
+                             "for the float64 reference itself there; use float64")
         self.lib = _native.load()
         if not torch.cuda.is_available():
             raise RuntimeError("curiousrl_b200 needs a CUDA device (B200); none is visible and there is no CPU fallback")

@@ -82,6 +82,50 @@ def make(tag):
     print("->", path, "%.0f KB" % (os.path.getsize(path) / 1024))
 
 
+F32_EPS = 6e-8                   # float32 unit round-off
+
+
+def make_f32(tag):
+    """What an FP32 solver can be expected to reproduce (north_star: FP32 mode <= 1e-4 relative on the final cost): the
+    reference re-solved with float32-sized relative noise on the outputs (K, k) and on the inputs (F, c) of its backward
+    pass, RUNS seeds each.  A problem whose own cost moves by more than 1e-4 under either is outside that bar by the
+    reference's own standard.  -> tests/golden/Envelope32_<tag>.npz"""
+    global INPUT_EPS
+    cls_name, kwargs, batch = mg.CONFIGS[tag]
+    base = np.load(os.path.join(ROOT, "tests", "golden", tag + ".npz"))
+    scenario = getattr(mg.ref_models, cls_name)(**kwargs)
+    algo = mg.BasiciLQR(max_line_search=mg.MAX_LINE_SEARCH)
+    algo.init(scenario)
+    rec = mg.Recorder(algo)
+    input_noise(rec)
+    saved, INPUT_EPS = INPUT_EPS, F32_EPS
+    x0s, targets = base["batch_x0"], base["batch_target"]
+    iters = np.zeros((batch, 2, RUNS), dtype=np.int32)
+    J = np.zeros((batch, 2, RUNS))
+    for b in range(batch):
+        for s in range(RUNS):
+            r = mg.run(algo, rec, x0s[b], targets[b], noise_seed=30000 + 1000 * b + s, noise_eps=F32_EPS)
+            iters[b, 0, s], J[b, 0, s] = r["iters"], r["J"]
+            rec.input_rng = np.random.default_rng(40000 + 1000 * b + s)
+            r = mg.run(algo, rec, x0s[b], targets[b])
+            rec.input_rng = None
+            iters[b, 1, s], J[b, 1, s] = r["iters"], r["J"]
+        Jref = float(base["batch_J"][b])
+        print("%s b=%d: reference %d iters | K,k 6e-8: iters %s dJ %.1e | F,c 6e-8: iters %s dJ %.1e" % (
+            tag, b, int(base["batch_iters"][b]), iters[b, 0].tolist(), np.abs(J[b, 0] - Jref).max() / abs(Jref),
+            iters[b, 1].tolist(), np.abs(J[b, 1] - Jref).max() / abs(Jref)), flush=True)
+    INPUT_EPS = saved
+    path = os.path.join(ROOT, "tests", "golden", "Envelope32_" + tag + ".npz")
+    np.savez_compressed(path, model=np.str_(cls_name), T=np.int64(scenario.T), eps=np.float64(F32_EPS), runs=np.int64(RUNS),
+                        iters=iters, J=J)
+    print("->", path)
+
+
 if __name__ == "__main__":
-    for tag in ("RoboticArm_T100", "RoboticArm_T200"):
-        make(tag)
+    which = sys.argv[1:] or ["f64", "f32"]
+    if "f64" in which:
+        for tag in ("RoboticArm_T100", "RoboticArm_T200"):
+            make(tag)
+    if "f32" in which:
+        for tag in ("TwoLink_T100", "ThreeLink_T100", "RoboticArm_T100"):
+            make_f32(tag)

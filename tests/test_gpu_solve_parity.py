@@ -113,27 +113,29 @@ def test_robotic_arm_envelope_rule(golden, tag, min_stable):
     assert s["passed"] == s["problems"], (s, [v for v in verdicts if not v["ok"]])
 
 
-def f32_stable_mask(g, tol=1e-4):
-    """Problems whose reference cost moves by <= tol when K, k carry float32-sized (6e-8) noise."""
-    return np.all(np.abs(g["noise32_J"] - g["batch_J"][:, None]) <= tol * np.abs(g["batch_J"][:, None]), axis=1)
-
-
-@pytest.mark.xfail(reason="pure-FP32 mode misses the 1e-4 cost bar on some problems; mixed-precision mode pending",
-                   strict=False)
-@pytest.mark.parametrize("tag", ["TwoLink_T100", "ThreeLink_T100"])
-def test_float32_final_cost(golden, tag):
-    """north_star FP32 bar: final cost <= 1e-4 relative, on problems where the reference itself is
-    reproducible to 1e-4 under float32-sized perturbations; everything must still terminate."""
-    g = golden(tag)
+@pytest.mark.parametrize("tag,min_subset", [("TwoLink_T100", 8), ("ThreeLink_T100", 6), ("RoboticArm_T100", 2)])
+def test_float32_final_cost(golden, tag, min_subset):
+    """north_star FP32 bar: final cost <= 1e-4 relative to the FP64 reference on every problem the reference itself
+    reproduces to 1e-4 under float32-sized noise on the inputs / outputs of its backward pass and decides clear of the
+    stopping criterion (tests/envelope_rule.py::f32_reproducible; fixtures from the unmodified reference); >= 90 % of
+    all noise-stable problems; everything terminates."""
+    import envelope_rule as er
+    g, e = golden(tag), golden("Envelope32_" + tag)
+    stable, subset = er.f32_reproducible(g, e)
+    assert subset.sum() >= min_subset
     algo = make_algo(str(g["model"]), int(g["T"]), dtype="float32")
     res = algo.solve_batch(g["batch_x0"], g["batch_target"]).to_host()
-    # pure-FP32 costs carry ~1e-6 relative noise, which ends slowly converging solves early (DESIGN.md,
-    # "FP32 mode"); the 1e-4 bar is asserted on problems the reference finishes within 30 iterations
-    stable = f32_stable_mask(g) & (g["batch_iters"] <= 30)
-    assert stable.sum() >= 0.4 * len(stable)
     err = np.abs(res.obj_fun_value - g["batch_J"]) / np.abs(g["batch_J"])
-    assert np.all(err[stable] <= 1e-3), err     # TODO(fp32): 1e-4 once the mixed-precision mode lands
+    assert np.all(err[subset] <= 1e-4), err[subset]
+    assert (err[stable] <= 1e-4).sum() >= 0.9 * stable.sum(), err[stable]
     assert np.all(res.converged == 1)
+
+
+def test_float32_is_refused_where_no_claim_can_be_made():
+    """RoboticArm beyond T = 100 is chaotic for the FP64 reference itself (0 of 8 seeded problems reproduce under 1e-15
+    noise at T = 200): no FP32 accuracy statement is possible there, so the mode is not offered."""
+    with pytest.raises(Exception, match="float32"):
+        make_algo("RoboticArmTracking", 200, dtype="float32")
 
 
 def test_reference_call_sequence(golden):

@@ -155,14 +155,22 @@ struct View {
 // multiple of 32 bytes), so a candidate's row is a run of whole 32-byte sectors: reading the current
 // trajectory touches only its own bytes (an element-interleaved layout costs a sector per element).
 // `on` = false turns the stores off (a candidate that is evaluated for its cost only).
-template <class R, int RS>
+// PAD0 / PAD1 (optional): storing element PAD0 - 1 also zeroes elements PAD0 .. PAD1 - 1, i.e. the padding behind a row,
+// so that every 32-byte sector of the row is written whole (a partly written sector costs the memory system a read of
+// the rest when the line leaves the L2; measured on the benchmark solve: 320 -> 306 ms, profiles/r02/ab_pad_rows.txt).
+template <class R, int RS, int PAD0 = 0, int PAD1 = 0>
 struct RowView {
     R* base;
     bool on = true;
     CRL_HD R* row(int t) const { return base + (size_t)t * RS; }
     CRL_HD static R ld(const R* row, int c) { return row[c]; }
     CRL_HD void st(R* row, int c, R v) const {
-        if (on) row[c] = v;
+        if (on) {
+            row[c] = v;
+            if (PAD1 > PAD0 && c == PAD0 - 1) {
+                CRL_UNROLL for (int p = PAD0; p < PAD1; ++p) row[p] = R(0);
+            }
+        }
     }
 };
 

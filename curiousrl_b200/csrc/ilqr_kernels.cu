@@ -451,13 +451,18 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
 // Candidates kCoopStore.. of a pass (step sizes accepted in < 1 % of the iterations) are evaluated for
 // their cost only; if one of them wins, the first lane of the group replays it into candidate 0.
 
+// row length of a candidate in the line-search buffers: D padded to a multiple of 4 reals (32 bytes in FP64)
+template <class Mdl>
+__host__ __device__ constexpr int coop_dp() { return (Mdl::D + 3) & ~3; }
+
 // closed-loop rollout for one step size from a stride-XS trajectory, stored to a stride-XS column;
 // returns its cost (a separate function so that it gets its own register allocation)
 template <class Mdl, class R, int RS>
 __device__ __noinline__ double coop_rollout(const R* X, const R* K, const R* k, R alpha, ParamRef<R> prm, Bounds<R> ub,
                                             int T, R* Xnew, bool store) {
     RowPrefetchFeed<Mdl, R, RS> feed(X, K, k);
-    return rollout_closed_f<Mdl, R>(feed, alpha, prm, ub, T, RowView<R, RS>{Xnew, store});
+    // stores the padding behind each row as well: every 32-byte sector of a candidate row is written whole
+    return rollout_closed_f<Mdl, R>(feed, alpha, prm, ub, T, RowView<R, RS, Mdl::D, coop_dp<Mdl>()>{Xnew, store});
 }
 
 // ---- two-phase rollout of a LONE trajectory (kinematic chains) ----------------------------------------------
@@ -603,9 +608,6 @@ template <int NT>
 struct CoopGeom {
     static constexpr int GL = (32 / NT) > 16 ? 16 : (32 / NT);   // line-search lanes (= candidates per pass) per trajectory
 };
-// row length of a candidate in the line-search buffers: D padded to a multiple of 4 reals (32 bytes in FP64)
-template <class Mdl>
-__host__ __device__ constexpr int coop_dp() { return (Mdl::D + 3) & ~3; }
 // reals between consecutive time steps of one candidate
 template <class Mdl, int NT>
 __host__ __device__ constexpr int coop_rs() { return CoopGeom<NT>::GL * coop_dp<Mdl>(); }

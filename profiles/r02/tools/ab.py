@@ -52,6 +52,12 @@ def worker(cases):
         it = int(res.iterations.sum())
         print("%-12s %-22s %9.2f ms %8.3f M traj-iter/s  iters %d  sha %s" % (lib, case, best, it / best / 1e3, it,
                                                                             h.hexdigest()[:16]), flush=True)
+        # -DCRL_PHASE_TIMERS builds: SM cycles per phase, summed over the warps (control-block words 8..16) of the LAST solve
+        ph = algo._dev._workspace[:256].view(torch.int64)[8:17].cpu().numpy()
+        if ph.any():
+            names = ["refill", "backward", "linesearch", "retire", "coop_wait", "coop_gather", "coop_backward",
+                     "coop_linesearch", "coop_output"]
+            print("    phases (M cycles): " + "  ".join("%s %.2f" % (n, v / 1e6) for n, v in zip(names, ph)), flush=True)
 
 
 if __name__ == "__main__":

@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int
 
 from . import build as _build
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MODEL_IDS = {"TwoLinkPlanarManipulator": 0, "ThreeLinkPlanarManipulator": 1, "RoboticArmTracking": 2}
 # the same scenarios under LogBarrieriLQR's cost (include/curiousrl_b200.h: CRL_*_BARRIER); FP64 only
 BARRIER_MODEL_IDS = {name: mid + 3 for name, mid in MODEL_IDS.items()}
@@ -25,7 +25,8 @@ STOPPING_IDS = {"relative": 0, "vanilla": 1}
 # every symbol include/curiousrl_b200.h declares (tests check the library exports all of them)
 EXPORTS = ("crl_abi_version", "crl_status_string", "crl_model_dims", "crl_model_default_bounds", "crl_model_bounds", "crl_rollout",
            "crl_cost", "crl_derivs", "crl_backward", "crl_backward_dense", "crl_update_traj", "crl_forward_pass",
-           "crl_solve_workspace_bytes", "crl_solve", "crl_solve_stages")
+           "crl_solve_workspace_bytes", "crl_solve", "crl_solve_stages", "crl_mlp_jacobian_workspace_bytes", "crl_mlp_jacobian",
+           "crl_smooth_time")
 
 
 class Problem(Structure):
@@ -64,9 +65,13 @@ def _declare(lib):
     lib.crl_solve_workspace_bytes.argtypes = [P, O]
     lib.crl_solve.argtypes = [P, O, vp, vp, c_int64, vp, vp, vp, vp, vp, vp, vp, vp, c_size_t, vp]
     lib.crl_solve_stages.argtypes = [P, O, c_int32, vp, vp, c_int64, vp, vp, vp, vp, vp, vp, vp, c_size_t, vp]
+    lib.crl_mlp_jacobian_workspace_bytes.restype = c_size_t
+    lib.crl_mlp_jacobian_workspace_bytes.argtypes = [c_int32, c_int32, c_int32, c_int32, c_int64, c_int32]
+    lib.crl_mlp_jacobian.argtypes = [c_int32, c_int32, c_int32, c_int32, c_int64] + [vp] * 11 + [c_size_t, c_int32, vp]
+    lib.crl_smooth_time.argtypes = [c_int64, c_int32, c_int32, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("crl_status_string", "crl_solve_workspace_bytes"):
+        if name not in ("crl_status_string", "crl_solve_workspace_bytes", "crl_mlp_jacobian_workspace_bytes"):
             fn.restype = c_int
 
 

@@ -13,7 +13,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libcuriousrl_b200.so")
-SOURCES = [os.path.join(CSRC, "ilqr_kernels.cu"), os.path.join(CSRC, "ilqr_generic.cu")]
+SOURCES = [os.path.join(CSRC, "ilqr_kernels.cu"), os.path.join(CSRC, "ilqr_generic.cu"), os.path.join(CSRC, "nn_jacobian.cu")]
 HEADERS = [os.path.join(CSRC, f) for f in ("ilqr_common.cuh", "ilqr_models.cuh", "ilqr_core.cuh", "ilqr_coop.cuh", "ilqr_generic.cuh",
                                                "ilqr_generated.cuh", "ilqr_generic_host.h")] + [
     os.path.join(os.path.dirname(PKG_DIR), "include", "curiousrl_b200.h")]
@@ -30,6 +30,7 @@ UNIT_HEADERS = {
     "ilqr_kernels.cu": ("ilqr_common.cuh", "ilqr_models.cuh", "ilqr_core.cuh", "ilqr_coop.cuh", "ilqr_generic_host.h"),
     "ilqr_generic.cu": ("ilqr_common.cuh", "ilqr_models.cuh", "ilqr_core.cuh", "ilqr_generic.cuh", "ilqr_generated.cuh",
                         "ilqr_generic_host.h"),
+    "nn_jacobian.cu": (),       # the learned-dynamics Jacobian (tcgen05 tensor-core kernels): only the C ABI header
 }
 
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CRL_ABI_VERSION 7
+#define CRL_ABI_VERSION 8
 
 typedef void* crl_stream_t; /* cudaStream_t */
 
@@ -183,6 +183,28 @@ int crl_solve_stages(const crl_problem_t* prob, const crl_solver_opts_t* opts, i
                      const void* u0, int64_t u0_stride_b, const double* J_init, void* X, double* J, int32_t* iters,
                      uint8_t* converged, int32_t* stage_iters, void* workspace, size_t workspace_bytes,
                      crl_stream_t stream);
+
+/* NNiLQRDynamicModel.eval_grad_dynamic_model (nn_ilqr.py:265-274) for a batch of points: value and Jacobian of the
+ * learned dynamics  y = W3 relu(W2 relu(W1 x + b1) + b2) + b3  (SmallNetwork / LargeNetwork, nn_ilqr.py:66-100, in eval
+ * mode, BatchNorm folded into W, b by the caller) at n_points rows x [n_points][d_in] - all FP32, like the reference's
+ * `.float().cuda()` tensors.
+ *  weights: w1 [h1][d_in], b1 [h1], w2 [h2][h1] and its transpose w2t [h1][h2], b2 [h2], w3 [n_out][h2], b3 [n_out];
+ *           h1, h2 multiples of 32 (pad with zero rows / columns), h2 <= 512, d_in <= 16, n_out <= 16;
+ *  out    : y [n_points][n_out], jac [n_points][n_out][d_in] (= F[t] of the reference, one [n][n+m] block per point);
+ *  impl   : 1 = tensor cores (tcgen05.mma kind::tf32, FP32 accumulation in tensor memory; the product path),
+ *           0 = FP32 CUDA cores (the checker of impl 1; a handful of points);
+ *  workspace: crl_mlp_jacobian_workspace_bytes() bytes, 256-byte aligned (sign-bit masks of the two hidden layers;
+ *           impl 0: also its activations).                                                                      */
+size_t crl_mlp_jacobian_workspace_bytes(int32_t d_in, int32_t h1, int32_t h2, int32_t n_out, int64_t n_points, int32_t impl);
+int crl_mlp_jacobian(int32_t d_in, int32_t h1, int32_t h2, int32_t n_out, int64_t n_points, const float* x, const float* w1,
+                     const float* b1, const float* w2, const float* w2t, const float* b2, const float* w3, const float* b3,
+                     float* y, float* jac, void* workspace, size_t workspace_bytes, int32_t impl, crl_stream_t stream);
+
+/* Linear filter along the time axis of [batch][horizon][width] FP64 arrays: out[b][t][:] = sum_t' G[t][t'] in[b][t'][:],
+ * G [horizon][horizon] row-major on the device.  NNiLQR.solve smooths the learned Jacobians with
+ * scipy.ndimage.gaussian_filter1d(F, sigma, axis=0) (nn_ilqr.py:379-380); G is that filter's matrix.  in != out.  */
+int crl_smooth_time(int64_t batch, int32_t horizon, int32_t width, const double* G, const double* in, double* out,
+                    crl_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), "symbol %s declared in the header is not exported" % name
     assert sorted(_native.EXPORTS) == names
-    assert lib.crl_abi_version() == _native.ABI_VERSION == 7
+    assert lib.crl_abi_version() == _native.ABI_VERSION == 8
 
 
 def test_model_tables_and_status_strings():

@@ -235,6 +235,7 @@ class NNiLQRDynamicModel(iLQRDynamicModel):
         model_path = logger.logger_path
         if model_path is None:
             raise Exception("Please call logger.set_folder_name(folder_name).set_is_use_logger(True) to enable the logger function!")
+        os.makedirs(model_path, exist_ok=True)
         path = os.path.join(model_path, model_name)
         if os.path.exists(path):
             logger.info("[+ +] Model file \"" + model_name + "\" exists. Loading....")

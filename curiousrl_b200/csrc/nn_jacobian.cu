@@ -15,13 +15,18 @@
 //                        whole width H2 (<= 512 columns), the epilogue adds b2, records the sign bits m2 and applies W3.
 //                        Writes y [S][n] and the bit masks m1 [S][H1/32], m2 [S][H2/32].
 //   mlp_jacobian_kernel  tile = 128 rows (s, r).  A block = W3 rows masked by m2 (generated in shared memory, never in
-//                        HBM), B block = W2^T slice; 128-column chunks of P accumulate in TMEM over H2; the epilogue
-//                        reads a chunk (tcgen05.ld), masks it by m1 and contracts it with W1 (K = 128, N = n + m: CUDA
-//                        cores, W1 in shared memory) into the per-thread Jacobian row.
-// Operands are staged by all 128 threads into double-buffered shared memory in the no-swizzle K-major canonical layout
-// (a block is `float4 blk[8 K-chunks][rows]`: 8-row x 16-byte core matrices, leading byte offset = rows * 16, stride
-// byte offset = 128), made visible to the tensor core with fence.proxy.async; completion comes back through
-// tcgen05.commit on mbarriers, so staging block b + 1 overlaps the MMAs of block b.
+//                        HBM), B block = W2^T slice (cp.async, one block ahead); 256-column chunks of P accumulate in one
+//                        of two TMEM accumulators over H2; the epilogue reads a chunk (tcgen05.ld), masks it by m1 and
+//                        contracts it with W1 (K = 256, N = n + m: CUDA cores, W1 in shared memory) into per-thread
+//                        Jacobian rows, spread over the blocks of the next chunk.  Warp-specialised: 8 producer /
+//                        epilogue warps and one MMA-issuer warp, coupled by mbarriers only (full / free per stage, acc /
+//                        accfree per accumulator), three shared-memory stages.
+// Operands are staged in the no-swizzle K-major canonical layout (a block is `float4 blk[8 K-chunks][rows]`: 8-row x
+// 16-byte core matrices, leading byte offset = rows * 16, stride byte offset = 128) and made visible to the tensor core
+// with fence.proxy.async; completion comes back through tcgen05.commit on mbarriers.
+// Measured on a B200 (profiles/r02/nn_jacobian.md): LargeNetwork (11 -> 800 -> 400 -> 8), 409,600 points: 16.7 ms
+// (forward 2.8 ms + Jacobian 13.9 ms) = 150 TFLOP/s; the FP32 CUDA-core path does 1.8 TFLOP/s.  The Jacobian kernel is
+// bound by its producers (about 3,000 cycles of staging + epilogue per block against 512 cycles of MMA), see the notes.
 //
 // `crl_mlp_jacobian(..., impl = 0)` is a plain FP32 CUDA-core evaluation of the same formulas (one thread per output
 // element, five small kernels): the checker of the tensor-core path in tests and the path for a handful of points.
@@ -250,128 +255,258 @@ mlp_forward_kernel(MlpDims dm, const float* __restrict__ x, const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ Jacobian
-// dynamic shared memory: A blocks 2 x [8][128] float4 | B blocks 2 x [8][128] float4 | W3 [n][h2] | W1 [h1][d] |
-// masks m2 [TS][h2/32], m1 [TS][h1/32] | barriers
-__global__ void __launch_bounds__(kThreads, 1)
+// One flat loop over the CTA's blocks b = (tile, chunk, K block): chunks are 256 hidden units of layer 1 wide (two TMEM
+// accumulators of 256 columns, used alternately), K blocks 32 hidden units of layer 2 deep.  Three shared-memory stages:
+// the B block of b + 1 is fetched with cp.async while A(b) is generated and the MMAs of b - 1 run; a stage is reused when
+// the commit of the MMAs that read it has arrived on its mbarrier.  The epilogue of chunk c (TMEM -> registers, mask by m1,
+// contraction with W1) is spread, one 32-column group per block, over the first blocks of chunk c + 1, so the tensor
+// core keeps working through it; only the last chunk of a tile is drained at once.
+// dynamic shared memory: A stages 3 x [8][128] float4 | B stages 3 x [8][256] float4 | W3 [n][h2 + 4] | W1 [h1][dp] |
+// masks 2 x (m2 [TS][h2/32], m1 [TS][h1/32]) | barriers
+constexpr int kJStages = 3;
+constexpr int kJChunk = 256;
+constexpr int kJThreads = 256;          // two threads per tile row
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kJThreads) : "memory"); }
+
+// Flat position of a block inside the CTA's work: (tile counter, chunk, K block) and stage / use counters, advanced
+// without divisions.
+struct JPos {
+    int ti, ch, kb, stage;
+    unsigned use;               // how often `stage` has been used before this block
+    __device__ void next(int nchunks, int nkb) {
+        if (++kb == nkb) { kb = 0; if (++ch == nchunks) { ch = 0; ++ti; } }
+        if (++stage == kJStages) { stage = 0; ++use; }
+    }
+};
+
+// Warps 0-7 (two threads per tile row) are PRODUCERS and EPILOGUE: they stage blocks and arrive on the stage's `full`
+// barrier; warp 8 is the MMA ISSUER: one lane waits for `full`, issues the block's tcgen05.mma's and commits them to the
+// stage's `free` barrier (and, after a chunk's last block, to the accumulator's `acc` barrier).  The producers never wait
+// for an MMA to be issued - only for the stage they refill to have been read and for a finished chunk to drain - so
+// staging, the tensor core and the epilogue overlap.  `accfree` tells the issuer that a drained accumulator may be
+// overwritten.
+__global__ void __launch_bounds__(kJThreads + 32, 1)
 mlp_jacobian_kernel(MlpDims dm, const float* __restrict__ w1, const float* __restrict__ w2t, const float* __restrict__ w3,
                     const uint32_t* __restrict__ m1, const uint32_t* __restrict__ m2, float* __restrict__ jac) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & 127, half = (tid >> 7) & 1;                        // two threads per tile row: K-chunks / column groups split
     const int d = dm.d, h1 = dm.h1, h2 = dm.h2, n = dm.n;
+    const int dp = (d + 3) & ~3;                                             // row pitch of W1 in shared memory
     const int TS = 128 / n;                                                  // points per tile
-    const int w1w = h1 / 32, w2w = h2 / 32;
-    float4* Ablk = reinterpret_cast<float4*>(smem);                          // [2][8][128]
-    float4* Bblk = Ablk + 2 * 8 * 128;                                       // [2][8][128]
-    float* W3s = reinterpret_cast<float*>(Bblk + 2 * 8 * 128);               // [n][h2]
-    float* W1s = W3s + n * h2;                                               // [h1][d]
-    uint32_t* m2s = reinterpret_cast<uint32_t*>(W1s + h1 * d);               // [TS][w2w]
-    uint32_t* m1s = m2s + TS * w2w;                                          // [TS][w1w]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(m1s + TS * w1w + ((TS * (w1w + w2w)) & 1));
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    const int w1w = h1 / 32, w2w = h2 / 32, mw = TS * (w1w + w2w);
+    const int w3p = h2 + 4;                                                  // row pitch of W3: the n rows a warp reads together fall into different banks
+    float4* Ablk = reinterpret_cast<float4*>(smem);                          // [3][8][128]
+    float4* Bblk = Ablk + kJStages * 8 * 128;                                // [3][8][256]
+    float* W3s = reinterpret_cast<float*>(Bblk + kJStages * 8 * kJChunk);    // [n][h2 + 4]
+    float* W1s = W3s + n * w3p;                                              // [h1][dp]
+    uint32_t* masks = reinterpret_cast<uint32_t*>(W1s + h1 * dp);            // [2][ m2 [TS][w2w] | m1 [TS][w1w] ]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(masks + 2 * mw + ((2 * mw) & 1));
+    uint64_t* bar_full = bars;                                               // [3] stage staged          (8 producer warps arrive)
+    uint64_t* bar_free = bars + kJStages;                                    // [3] stage read            (tcgen05.commit)
+    uint64_t* bar_acc = bars + 2 * kJStages;                                 // [2] chunk accumulated     (tcgen05.commit)
+    uint64_t* bar_accfree = bars + 2 * kJStages + 2;                         // [2] accumulator drained   (8 producer warps arrive)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kJStages + 4);
+    float* red = reinterpret_cast<float*>(tmem_slot + 2);                    // [128][kMaxD] partial rows of the second half
 
-    for (int i = tid; i < n * h2; i += kThreads) W3s[i] = w3[i];
-    for (int i = tid; i < h1 * d; i += kThreads) W1s[i] = w1[i];
+    if (tid < kJThreads) {
+        for (int i = tid; i < n * h2; i += kJThreads) W3s[(i / h2) * w3p + i % h2] = w3[i];
+        for (int i = tid; i < h1 * dp; i += kJThreads) {
+            const int h = i / dp, j = i - h * dp;
+            W1s[i] = j < d ? w1[h * d + j] : 0.0f;
+        }
+    }
     if (tid == 0) {
-        mbar_init(bars + 0, 1);
-        mbar_init(bars + 1, 1);
-        mbar_init(bars + 2, 1);
+        for (int i = 0; i < kJStages; ++i) { mbar_init(bar_full + i, kJThreads / 32); mbar_init(bar_free + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_acc + i, 1); mbar_init(bar_accfree + i, kJThreads / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) tmem_alloc(tmem_slot, 128);
+    if (warp == 0) tmem_alloc(tmem_slot, 2 * kJChunk);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const int nkb = h2 / kKB;
-    const int nchunks = (h1 + 127) / 128;
+    const int nchunks = (h1 + kJChunk - 1) / kJChunk;
     const long long tiles = (dm.S + TS - 1) / TS;
-    const int ls = tid / n, out = tid - ls * n;                              // this thread's row: point ls, output `out`
-    unsigned blk = 0, chunk_no = 0;
+    const int my_tiles = tiles > blockIdx.x ? (int)((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    const long long total = (long long)my_tiles * nchunks * nkb;
 
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const long long s0 = tile * TS;
-        const bool valid = ls < TS && s0 + ls < dm.S;
-        __syncthreads();                                                     // the previous tile's readers of the masks
-        for (int i = tid; i < TS * w2w; i += kThreads) {
-            const long long sp = s0 + i / w2w;
-            m2s[i] = sp < dm.S ? m2[sp * w2w + i % w2w] : 0u;
+    if (warp == kJThreads / 32) {
+        // ================================================================ MMA issuer (one lane)
+        if ((tid & 31) == 0) {
+            JPos p{0, 0, 0, 0, 0u};
+            unsigned acc_uses[2] = {0u, 0u};                                 // chunks started per accumulator
+            for (long long b = 0; b < total; ++b, p.next(nchunks, nkb)) {
+                const int a = p.ch & 1;
+                if (p.kb == 0) {
+                    if (acc_uses[a] >= 1) mbar_wait(bar_accfree + a, (acc_uses[a] - 1) & 1u);   // the previous chunk on it is drained
+                    ++acc_uses[a];
+                }
+                mbar_wait(bar_full + p.stage, p.use & 1u);
+                tc_fence_after();
+                const int n0 = p.ch * kJChunk, nc = h1 - n0 < kJChunk ? h1 - n0 : kJChunk;
+                const uint32_t idesc = instr_desc(nc);
+                const uint32_t a0 = smem_u32(Ablk + p.stage * (8 * 128)), b0 = smem_u32(Bblk + p.stage * (8 * kJChunk));
+#pragma unroll
+                for (int st = 0; st < kKB / 8; ++st)
+                    tc_mma_tf32(tmem + a * kJChunk, smem_desc(a0 + st * 2 * (128 * 16), 128 * 16),
+                                smem_desc(b0 + st * 2 * (kJChunk * 16), kJChunk * 16), idesc, p.kb > 0 || st > 0);
+                tc_commit(bar_free + p.stage);
+                if (p.kb == nkb - 1) tc_commit(bar_acc + a);
+            }
         }
-        for (int i = tid; i < TS * w1w; i += kThreads) {
-            const long long sp = s0 + i / w1w;
-            m1s[i] = sp < dm.S ? m1[sp * w1w + i % w1w] : 0u;
-        }
-        __syncthreads();
+    } else {
+        // ================================================================ producers + epilogue
+        const int ls = row / n, out = row - ls * n;                          // this thread's row: point ls, output `out`
+        const float* my_w3 = W3s + out * w3p;
+        auto load_masks = [&](long long tile, int slot) {
+            const long long s0 = tile * TS;
+            uint32_t* dst = masks + slot * mw;
+            for (int i = tid; i < TS * w2w; i += kJThreads) {
+                const long long sp = s0 + i / w2w;
+                dst[i] = sp < dm.S ? m2[sp * w2w + i % w2w] : 0u;
+            }
+            for (int i = tid; i < TS * w1w; i += kJThreads) {
+                const long long sp = s0 + i / w1w;
+                dst[TS * w2w + i] = sp < dm.S ? m1[sp * w1w + i % w1w] : 0u;
+            }
+        };
+        // B block of position q: rows = hidden units of the chunk, 32 K values each, fetched asynchronously
+        auto issue_b = [&](const JPos& q) {
+            if (q.use >= 1) mbar_wait(bar_free + q.stage, (q.use - 1) & 1u);   // the MMAs that read the stage are done
+            const int n0 = q.ch * kJChunk, nc = h1 - n0 < kJChunk ? h1 - n0 : kJChunk;
+            float4* Bb = Bblk + q.stage * (8 * kJChunk);
+            for (int br = tid; br < nc; br += kJThreads) {
+                const float* src = w2t + (size_t)(n0 + br) * h2 + q.kb * kKB;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) cp_async16(Bb + c * kJChunk + br, src + c * 4);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
         float acc[kMaxD];
+        unsigned acc_done[2] = {0u, 0u};                                     // chunks drained per accumulator
+        int pend_chunk = -1, pend_group = 0, pend_groups = 0;               // epilogue in progress: chunk, next group, groups
+        // one 32-column group of the epilogue of chunk `ch`: P masked by m1, contracted with W1
+        auto epilogue_group = [&](int ch, int g, const uint32_t* my_m1) {
+            const int n0 = ch * kJChunk;
+            float v[32];
+            tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (ch & 1) * kJChunk + g * 32, v);
+            const uint32_t mb = my_m1[(n0 >> 5) + g];
 #pragma unroll
-        for (int j = 0; j < kMaxD; ++j) acc[j] = 0.0f;
-        const uint32_t* my_m2 = m2s + (valid ? ls : 0) * w2w;
-        const uint32_t* my_m1 = m1s + (valid ? ls : 0) * w1w;
-        const float* my_w3 = W3s + out * h2;
-
-        for (int ch = 0; ch < nchunks; ++ch, ++chunk_no) {
-            const int n0 = ch * 128;
-            const int nc = h1 - n0 < 128 ? h1 - n0 : 128;                    // columns of this chunk (multiple of 32)
-            const uint32_t idesc = instr_desc(nc);
-            for (int kb = 0; kb < nkb; ++kb, ++blk) {
-                const int buf = blk & 1;
-                if (blk >= 2) mbar_wait(bars + buf, ((blk >> 1) - 1) & 1);
-                // A block: row (s, r) of G2 = W3[r, :] masked by m2[s, :], 32 hidden units of layer 2
-                float4* Ab = Ablk + buf * (8 * 128);
-                const uint32_t bits = valid ? my_m2[kb] : 0u;
+            for (int i = 0; i < 32; ++i) {
+                const float pv = (mb >> i) & 1u ? v[i] : 0.0f;
+                const float4* wr = reinterpret_cast<const float4*>(W1s + (n0 + g * 32 + i) * dp);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float4 w = *reinterpret_cast<const float4*>(my_w3 + kb * kKB + c * 4);
-                    Ab[c * 128 + tid] = make_float4((bits >> (c * 4 + 0)) & 1u ? w.x : 0.0f, (bits >> (c * 4 + 1)) & 1u ? w.y : 0.0f,
-                                                    (bits >> (c * 4 + 2)) & 1u ? w.z : 0.0f, (bits >> (c * 4 + 3)) & 1u ? w.w : 0.0f);
-                }
-                // B block: rows = hidden units n0 .. n0 + nc of layer 1, K = this block's 32 units of layer 2 (W2^T [h1][h2])
-                float4* Bb = Bblk + buf * (8 * 128);
-                if (tid < nc) {
-                    const float4* src = reinterpret_cast<const float4*>(w2t + (size_t)(n0 + tid) * h2 + kb * kKB);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) Bb[c * 128 + tid] = __ldg(src + c);
-                }
-                proxy_fence();
-                __syncthreads();
-                if (tid == 0) {
-                    tc_fence_after();
-                    const uint32_t a0 = smem_u32(Ab), b0 = smem_u32(Bb);
-#pragma unroll
-                    for (int st = 0; st < kKB / 8; ++st)
-                        tc_mma_tf32(tmem, smem_desc(a0 + st * 2 * (128 * 16), 128 * 16),
-                                    smem_desc(b0 + st * 2 * (128 * 16), 128 * 16), idesc, kb > 0 || st > 0);
-                    tc_commit(bars + buf);
-                    if (kb == nkb - 1) tc_commit(bars + 2);
-                }
+                for (int q = 0; q < kMaxD / 4; ++q)
+                    if (q * 4 < d) {
+                        const float4 w = wr[q];
+                        acc[q * 4 + 0] = fmaf(pv, w.x, acc[q * 4 + 0]);
+                        acc[q * 4 + 1] = fmaf(pv, w.y, acc[q * 4 + 1]);
+                        acc[q * 4 + 2] = fmaf(pv, w.z, acc[q * 4 + 2]);
+                        acc[q * 4 + 3] = fmaf(pv, w.w, acc[q * 4 + 3]);
+                    }
             }
-            // epilogue of the chunk: P[row, n0 .. n0 + nc) masked by m1, contracted with W1
-            mbar_wait(bars + 2, chunk_no & 1);
+        };
+        // wait until chunk `ch` is accumulated / tell the issuer that it is drained
+        auto drain_begin = [&](int ch) {
+            mbar_wait(bar_acc + (ch & 1), acc_done[ch & 1] & 1u);
+            ++acc_done[ch & 1];
             tc_fence_after();
-            for (int g = 0; g < nc / 32; ++g) {
-                float v[32];
-                tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + g * 32, v);
-                const uint32_t mb = my_m1[(n0 >> 5) + g];
+        };
+        auto drain_end = [&](int ch) {
+            tc_fence_before();
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(bar_accfree + (ch & 1));
+        };
+
+        JPos p{0, 0, 0, 0, 0u}, q{0, 0, 0, 0, 0u};                           // current block / the block whose B is fetched
+        if (total > 0) {
+            load_masks(blockIdx.x, 0);
+            issue_b(q);
+            q.next(nchunks, nkb);
+        }
+        producers_sync();
+        for (long long b = 0; b < total; ++b, p.next(nchunks, nkb)) {
+            const long long tile = blockIdx.x + (long long)p.ti * gridDim.x;
+            const int slot = p.ti & 1;
+            const bool valid = ls < TS && tile * TS + ls < dm.S;
+            const uint32_t* my_m2 = masks + slot * mw + (valid ? ls : 0) * w2w;
+            const uint32_t* my_m1 = masks + slot * mw + TS * w2w + (valid ? ls : 0) * w1w;
+            if (p.ch == 0 && p.kb == 0) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float p = (mb >> i) & 1u ? v[i] : 0.0f;
-                    const float* wr = W1s + (n0 + g * 32 + i) * d;
+                for (int j = 0; j < kMaxD; ++j) acc[j] = 0.0f;
+                if (p.ti + 1 < my_tiles) load_masks(tile + gridDim.x, slot ^ 1);   // read from the next tile's first block on
+            }
+            if (b + 1 < total) {
+                issue_b(q);
+                q.next(nchunks, nkb);
+            }
+            // A block: row (s, r) of G2 = W3[r, :] masked by m2[s, :], 32 hidden units of layer 2 (the stage is free: its
+            // previous use was waited for when this block's B was issued)
+            float4* Ab = Ablk + p.stage * (8 * 128);
+            const uint32_t bits = valid ? my_m2[p.kb] : 0u;
 #pragma unroll
-                    for (int j = 0; j < kMaxD; ++j)
-                        if (j < d) acc[j] = fmaf(p, wr[j], acc[j]);
+            for (int cc = 0; cc < 4; ++cc) {
+                const int c = half * 4 + cc;
+                const float4 w = *reinterpret_cast<const float4*>(my_w3 + p.kb * kKB + c * 4);
+                Ab[c * 128 + row] = make_float4((bits >> (c * 4 + 0)) & 1u ? w.x : 0.0f, (bits >> (c * 4 + 1)) & 1u ? w.y : 0.0f,
+                                                (bits >> (c * 4 + 2)) & 1u ? w.z : 0.0f, (bits >> (c * 4 + 3)) & 1u ? w.w : 0.0f);
+            }
+            if (b + 1 < total) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            proxy_fence();
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(bar_full + p.stage);
+            // the epilogue of the previous chunk, one pair of groups per block (all that is left at the chunk's last block)
+            if (pend_chunk >= 0) {
+                if (pend_group == 0) drain_begin(pend_chunk);
+                do {
+                    if (pend_group + half < pend_groups) epilogue_group(pend_chunk, pend_group + half, my_m1);
+                    pend_group += 2;
+                } while (pend_group < pend_groups && p.kb == nkb - 1);
+                if (pend_group >= pend_groups) {
+                    drain_end(pend_chunk);
+                    pend_chunk = -1;
                 }
             }
-            tc_fence_before();
-            __syncthreads();                                                 // the next chunk overwrites the accumulator
-        }
-        if (valid) {
-            float* dst = jac + ((s0 + ls) * n + out) * d;
+            if (p.kb == nkb - 1) {
+                const int n0 = p.ch * kJChunk, nc = h1 - n0 < kJChunk ? h1 - n0 : kJChunk;
+                if (p.ch == nchunks - 1) {
+                    // last chunk of the tile: drain it now and write the rows out
+                    drain_begin(p.ch);
+                    for (int g = half; g < nc / 32; g += 2) epilogue_group(p.ch, g, my_m1);
+                    drain_end(p.ch);
+                    if (half == 1) {
 #pragma unroll
-            for (int j = 0; j < kMaxD; ++j)
-                if (j < d) dst[j] = acc[j];
+                        for (int j = 0; j < kMaxD; ++j) red[row * kMaxD + j] = acc[j];
+                    }
+                    producers_sync();
+                    if (half == 0 && valid) {
+                        float* dst = jac + ((tile * TS + ls) * n + out) * d;
+#pragma unroll
+                        for (int j = 0; j < kMaxD; ++j)
+                            if (j < d) dst[j] = acc[j] + red[row * kMaxD + j];
+                    }
+                    producers_sync();                                         // `red` and the other mask slot are rewritten next
+                } else {
+                    pend_chunk = p.ch;
+                    pend_group = 0;
+                    pend_groups = nc / 32;
+                }
+            }
         }
     }
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 128);
+    if (warp == 0) tmem_dealloc(tmem, 2 * kJChunk);
 }
 
 // ------------------------------------------------------------------------------------------------ FP32 CUDA-core path
@@ -549,8 +684,9 @@ int crl_mlp_jacobian(int32_t d_in, int32_t h1, int32_t h2, int32_t n_out, int64_
         const size_t f_smem = (size_t)2 * 8 * 128 * 16 + (size_t)2 * 8 * h2 * 16 + ((size_t)h1 * d_in + h1 + (size_t)n_out * h2 + h2) * 4 +
                               3 * 8 + 16;
         const int TS = 128 / n_out;
-        const size_t j_smem = (size_t)4 * 8 * 128 * 16 + ((size_t)n_out * h2 + (size_t)h1 * d_in) * 4 +
-                              ((size_t)TS * (h1 / 32 + h2 / 32) + 1) * 4 + 3 * 8 + 16;
+        const int dp = (d_in + 3) & ~3;
+        const size_t j_smem = (size_t)kJStages * 8 * (128 + kJChunk) * 16 + ((size_t)n_out * (h2 + 4) + (size_t)h1 * dp) * 4 +
+                              ((size_t)2 * TS * (h1 / 32 + h2 / 32) + 1) * 4 + (2 * kJStages + 4) * 8 + 16 + (size_t)128 * kMaxD * 4;
         if (f_smem > 227 * 1024 || j_smem > 227 * 1024) {
             cudaSetDevice(prev);
             return CRL_ERR_BAD_ARGUMENT;
@@ -561,7 +697,7 @@ int crl_mlp_jacobian(int32_t d_in, int32_t h1, int32_t h2, int32_t n_out, int64_
             const long long f_tiles = (n_points + 127) / 128, j_tiles = (n_points + TS - 1) / TS;
             mlp_forward_kernel<<<(unsigned)(f_tiles < sms ? f_tiles : sms), kThreads, f_smem, s>>>(dm, x, w1, b1, w2, b2, w3, b3, y, m1,
                                                                                                   m2);
-            mlp_jacobian_kernel<<<(unsigned)(j_tiles < sms ? j_tiles : sms), kThreads, j_smem, s>>>(dm, w1, w2t, w3, m1, m2, jac);
+            mlp_jacobian_kernel<<<(unsigned)(j_tiles < sms ? j_tiles : sms), kJThreads + 32, j_smem, s>>>(dm, w1, w2t, w3, m1, m2, jac);
             e = cudaGetLastError();
         }
     }

@@ -7,6 +7,7 @@ Random network in eval mode (BatchNorm with non-trivial running statistics), ran
 nn_ilqr.py:265-274), the tensor-core path (impl 1) against impl 0, and the time of both.
 """
 import argparse
+import hashlib
 import os
 import sys
 
@@ -64,6 +65,7 @@ for S in a.points:
             float((j1 - j0).norm() / j0.norm()),
             float(((j1 - j0).flatten(1).norm(dim=1) / j0.flatten(1).norm(dim=1).clamp_min(1e-20)).max()),
             float((y1 - y0).norm() / y0.norm()))
+    line += "  sha(jac1) %s" % hashlib.sha256(j1.cpu().numpy().tobytes()).hexdigest()[:12]
     for impl in ((0, 1) if S <= 20000 else (1,)):
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         folded.jacobian(x, impl=impl)

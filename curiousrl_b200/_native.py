@@ -46,33 +46,36 @@ _lib = None
 
 
 def _declare(lib):
+    """argtypes / restype of every entry point the library has (a run-time compiled scenario library, jit.py, exports the
+    iLQR part of the ABI only)."""
     P, O = POINTER(Problem), POINTER(SolverOpts)
     vp = c_void_p
-    lib.crl_abi_version.restype = c_int
-    lib.crl_status_string.restype = c_char_p
-    lib.crl_status_string.argtypes = [c_int]
-    lib.crl_model_dims.argtypes = [c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]
-    lib.crl_model_default_bounds.argtypes = [c_int, POINTER(c_double), POINTER(c_double)]
-    lib.crl_model_bounds.argtypes = [c_int, POINTER(c_double), POINTER(c_double)]
-    lib.crl_rollout.argtypes = [P, vp, vp, c_int64, vp, vp, vp]
-    lib.crl_cost.argtypes = [P, vp, vp, vp]
-    lib.crl_derivs.argtypes = [P, vp, vp, vp, vp, vp]
-    lib.crl_backward.argtypes = [P, vp, vp, vp, vp]
-    lib.crl_backward_dense.argtypes = [c_int32, c_int32, c_int32, c_int64, c_int32, vp, vp, vp, vp, vp, vp]
-    lib.crl_update_traj.argtypes = [P, vp, vp, vp, c_double, vp, vp, vp]
-    lib.crl_forward_pass.argtypes = [P, O, vp, vp, vp, vp, vp, vp, vp, vp, vp]
-    lib.crl_solve_workspace_bytes.restype = c_size_t
-    lib.crl_solve_workspace_bytes.argtypes = [P, O]
-    lib.crl_solve.argtypes = [P, O, vp, vp, c_int64, vp, vp, vp, vp, vp, vp, vp, vp, c_size_t, vp]
-    lib.crl_solve_stages.argtypes = [P, O, c_int32, vp, vp, c_int64, vp, vp, vp, vp, vp, vp, vp, c_size_t, vp]
-    lib.crl_mlp_jacobian_workspace_bytes.restype = c_size_t
-    lib.crl_mlp_jacobian_workspace_bytes.argtypes = [c_int32, c_int32, c_int32, c_int32, c_int64, c_int32]
-    lib.crl_mlp_jacobian.argtypes = [c_int32, c_int32, c_int32, c_int32, c_int64] + [vp] * 11 + [c_size_t, c_int32, vp]
-    lib.crl_smooth_time.argtypes = [c_int64, c_int32, c_int32, vp, vp, vp, vp]
-    for name in EXPORTS:
-        fn = getattr(lib, name)
-        if name not in ("crl_status_string", "crl_solve_workspace_bytes", "crl_mlp_jacobian_workspace_bytes"):
-            fn.restype = c_int
+    table = {
+        "crl_abi_version": (c_int, []),
+        "crl_status_string": (c_char_p, [c_int]),
+        "crl_model_dims": (c_int, [c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+        "crl_model_default_bounds": (c_int, [c_int, POINTER(c_double), POINTER(c_double)]),
+        "crl_model_bounds": (c_int, [c_int, POINTER(c_double), POINTER(c_double)]),
+        "crl_rollout": (c_int, [P, vp, vp, c_int64, vp, vp, vp]),
+        "crl_cost": (c_int, [P, vp, vp, vp]),
+        "crl_derivs": (c_int, [P, vp, vp, vp, vp, vp]),
+        "crl_backward": (c_int, [P, vp, vp, vp, vp]),
+        "crl_backward_dense": (c_int, [c_int32, c_int32, c_int32, c_int64, c_int32, vp, vp, vp, vp, vp, vp]),
+        "crl_update_traj": (c_int, [P, vp, vp, vp, c_double, vp, vp, vp]),
+        "crl_forward_pass": (c_int, [P, O, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "crl_solve_workspace_bytes": (c_size_t, [P, O]),
+        "crl_solve": (c_int, [P, O, vp, vp, c_int64, vp, vp, vp, vp, vp, vp, vp, vp, c_size_t, vp]),
+        "crl_solve_stages": (c_int, [P, O, c_int32, vp, vp, c_int64, vp, vp, vp, vp, vp, vp, vp, c_size_t, vp]),
+        "crl_mlp_jacobian_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32, c_int64, c_int32]),
+        "crl_mlp_jacobian": (c_int, [c_int32, c_int32, c_int32, c_int32, c_int64] + [vp] * 11 + [c_size_t, c_int32, vp]),
+        "crl_smooth_time": (c_int, [c_int64, c_int32, c_int32, vp, vp, vp, vp]),
+    }
+    assert set(table) == set(EXPORTS)
+    for name, (restype, argtypes) in table.items():
+        fn = getattr(lib, name, None)
+        if fn is not None:
+            fn.restype = restype
+            fn.argtypes = argtypes
 
 
 def load():

@@ -40,11 +40,16 @@ class BatchResult:
 
 class DeviceModel:
     def __init__(self, model_name: str, T: int, u_lo: float, u_hi: float, dtype: str = "float64", device=None,
-                 barrier: bool = False, bounds=None):
+                 barrier: bool = False, bounds=None, scenario=None):
+        """`scenario`: the scenario object - needed only for a scenario without a precompiled device model, which is
+        then generated from its sympy expressions and compiled at run time (curiousrl_b200/jit.py)."""
         self.generic = model_name in _native.GENERIC_MODEL_IDS      # generated device model: FP64, bounds compiled in
-        if model_name not in _native.MODEL_IDS and not self.generic:
-            raise Exception('Scenario "%s" has no device model in curiousrl_b200 (supported: %s); '
-                            "there is no CPU fallback." % (model_name, ", ".join(list(_native.MODEL_IDS) + list(_native.GENERIC_MODEL_IDS))))
+        self.jit = model_name not in _native.MODEL_IDS and not self.generic
+        if self.jit and scenario is None:
+            raise Exception('Scenario "%s" has no precompiled device model in curiousrl_b200 (%s) and no scenario object was '
+                            "given to compile one from; there is no CPU fallback." % (
+                                model_name, ", ".join(list(_native.MODEL_IDS) + list(_native.GENERIC_MODEL_IDS))))
+        self.generic = self.generic or self.jit
         if self.generic and dtype != "float64":
             raise ValueError('the generated device model of "%s" is compiled for float64 only' % model_name)
         if dtype not in _TORCH_DTYPE:
@@ -54,16 +59,25 @@ class DeviceModel:
             # O(1)); north_star's FP32 bar (1e-4 on the final cost) cannot be stated there, so the mode is not offered
             raise ValueError('dtype="float32" is not offered for RoboticArmTracking with T > 100: the scenario is chaotic '
                              "for the float64 reference itself there; use float64")
-        self.lib = _native.load()
+        if self.jit:
+            from ... import jit as _jit
+            self.lib, self.lib_path = _jit.compile_scenario(scenario)
+        else:
+            self.lib = _native.load()
         if not torch.cuda.is_available():
             raise RuntimeError("curiousrl_b200 needs a CUDA device (B200); none is visible and there is no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         if barrier and dtype != "float64":
             raise ValueError("the log-barrier cost is compiled for float64 only")
         self.model_name = model_name
-        self.model_id = ((_native.GENERIC_BARRIER_MODEL_IDS if barrier else _native.GENERIC_MODEL_IDS) if self.generic else
-                         _native.BARRIER_MODEL_IDS if barrier else _native.MODEL_IDS)[model_name]
-        self.n, self.m, self.p = _native.model_dims(self.model_id)
+        if self.jit:
+            self.model_id = 101 if barrier else 100                    # CRL_GEN_USER_BARRIER / CRL_GEN_USER
+        else:
+            self.model_id = ((_native.GENERIC_BARRIER_MODEL_IDS if barrier else _native.GENERIC_MODEL_IDS) if self.generic else
+                             _native.BARRIER_MODEL_IDS if barrier else _native.MODEL_IDS)[model_name]
+        n_, m_, p_ = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _native.check(self.lib.crl_model_dims(self.model_id, n_, m_, p_), "crl_model_dims")
+        self.n, self.m, self.p = n_.value, m_.value, p_.value
         self.d = self.n + self.m
         self.T = int(T)
         self.dtype_name, self.dtype, self.dtype_id = dtype, _TORCH_DTYPE[dtype], _native.DTYPE_IDS[dtype]

@@ -86,7 +86,13 @@ class LogBarrieriLQR(iLQRWrapper):
         n = int(scenario.init_state.shape[0])
         T = int(scenario.init_action.shape[0])
         self._generic = scenario.name in _native.GENERIC_MODEL_IDS
-        if self._generic:
+        jit = not self._generic and scenario.name not in _native.MODEL_IDS
+        if jit:
+            # any other scenario: plain and barrier models are generated from its sympy expressions and compiled now
+            # (curiousrl_b200/jit.py); the barrier sits on every finite bound of the scenario's own box
+            self._generic = True
+            lo = hi = 0.0
+        elif self._generic:
             # generated device model: the barrier sits on every finite bound of the compiled-in box, states included
             compiled = np.asarray(_native.model_bounds(_native.GENERIC_MODEL_IDS[scenario.name]), dtype=np.float64)
             if compiled.shape != constr.shape or not np.array_equal(compiled, constr):
@@ -100,8 +106,8 @@ class LogBarrieriLQR(iLQRWrapper):
             lo, hi = _native.model_default_bounds(_native.MODEL_IDS[scenario.name])
             if not (np.all(constr[n:, 0] == lo) and np.all(constr[n:, 1] == hi)):
                 raise Exception('Scenario "%s": the barrier cost is compiled for the action box [%g, %g]' % (scenario.name, lo, hi))
-        self._dev = DeviceModel(scenario.name, T, lo, hi, device=self._device, barrier=True)
-        self._real_dev = DeviceModel(scenario.name, T, lo, hi, device=self._device)
+        self._dev = DeviceModel(scenario.name, T, lo, hi, device=self._device, barrier=True, scenario=scenario if jit else None)
+        self._real_dev = DeviceModel(scenario.name, T, lo, hi, device=self._device, scenario=scenario if jit else None)
         self._dynamic_model = iLQRDynamicModel(self._dev, scenario.init_state, scenario.init_action, self)
         self._real_add_param = scenario.add_param          # None for a scenario without add_param
         if scenario.add_param is None:

@@ -275,6 +275,10 @@ class BasiciLQR(iLQRWrapper):
                 raise Exception('Scenario "%s" does not have the shape of the device model' % scenario.name)
             self._dev = DeviceModel(scenario.name, T, 0.0, 0.0, dtype=self._dtype, device=self._device,
                                     bounds=None if np.array_equal(compiled, constr) else constr)
+        elif scenario.name not in _native.MODEL_IDS:
+            # any other DynamicModelWrapper (basic_ilqr.py:50-66 takes them all): its device model is generated from the
+            # scenario's sympy expressions and compiled now (curiousrl_b200/jit.py; cached in-tree); box compiled in
+            self._dev = DeviceModel(scenario.name, T, 0.0, 0.0, dtype=self._dtype, device=self._device, scenario=scenario)
         else:
             if not (np.all(constr[:n, 0] == -np.inf) and np.all(constr[:n, 1] == np.inf)):
                 raise Exception('Scenario "%s": finite state bounds are not supported by the device models' % scenario.name)

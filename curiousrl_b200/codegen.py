@@ -70,8 +70,8 @@ def _fmt_bound(v):
     return repr(float(v))
 
 
-def generate_struct(scenario) -> str:
-    """The `Gen<name>` struct text of one scenario object."""
+def generate_struct(scenario, name=None) -> str:
+    """The `Gen<name>` struct text of one scenario object (name: the scenario's class name unless given)."""
     printer = _DevicePrinter()
     xu = list(scenario.x_u_var)
     n = int(scenario.init_state.shape[0])
@@ -87,7 +87,7 @@ def generate_struct(scenario) -> str:
     g = sp.derive_by_array(l, xu)
     H = np.asarray(sp.derive_by_array(g, xu)) + 1e-100 * np.eye(d)                 # ilqr_obj_fun.py:51
     constr = np.asarray(scenario.constr, dtype=np.float64)
-    name = type(scenario).__name__
+    name = type(scenario).__name__ if name is None else name
     out = ["// %s  (n = %d, m = %d, p = %d)" % (name, n, m, p),
            "struct Gen%s {" % name,
            "    static constexpr int N = %d, M = %d, D = %d, P = %d;" % (n, m, d, p),
@@ -109,7 +109,7 @@ def generate_struct(scenario) -> str:
     return "\n".join(out)
 
 
-def generate_barrier_struct(scenario) -> str:
+def generate_barrier_struct(scenario, name=None) -> str:
     """`Gen<name>Barrier`: the scenario under LogBarrieriLQR's cost (log_barrier_ilqr.py:84-101) - every finite bound,
     state bounds included, adds (-1/t) log(-(lo - x_u[i])) / (-1/t) log(-(x_u[i] - hi)).  Dynamics and box are the
     plain model's; the parameter row is (the scenario's add_param columns, t, t0) with t0 = the stale barrier
@@ -128,7 +128,7 @@ def generate_barrier_struct(scenario) -> str:
             l = l + (-1 / t_var) * sp.log(-(xu[i] - c[1]))
     g = sp.derive_by_array(l, xu)
     H = np.asarray(sp.derive_by_array(g, xu)) + 1e-100 * np.eye(d)
-    name = type(scenario).__name__
+    name = type(scenario).__name__ if name is None else name
     ax, ap = _aliases(xu, "x"), _aliases(pv + [t_var], "p")
     out = ["// %s under the log-barrier cost  (parameter row: %d scenario columns, t, t0)" % (name, len(pv)),
            "struct Gen%sBarrier : Gen%s {" % (name, name),
@@ -144,6 +144,20 @@ def generate_barrier_struct(scenario) -> str:
     out += ax + ap + _emit_assignments(printer, "C", [H[i, j] for i in range(d) for j in range(d)])
     out += ["    }", "};", ""]
     return "\n".join(out)
+
+
+HEADER_PREAMBLE = ['#pragma once', '#include <math.h>', '',
+                   '#if defined(__CUDACC__)', '#define CRL_GEN_FN __host__ __device__ __forceinline__ static',
+                   '#else', '#define CRL_GEN_FN inline static', '#endif',
+                   '#define CRL_GEN_INF (__builtin_huge_val())', '', 'namespace crl {', '']
+
+
+def generate_user_header(scenario) -> str:
+    """Header of ONE scenario for the run-time compiled library (jit.py): structs GenUser / GenUserBarrier."""
+    head = ['// GENERATED by curiousrl_b200/codegen.py from a %s object at run time (sympy %s).' % (type(scenario).__name__,
+                                                                                                  sp.__version__)]
+    body = [generate_struct(scenario, "User"), generate_barrier_struct(scenario, "User")]
+    return "\n".join(head + HEADER_PREAMBLE + body + ["}  // namespace crl", ""])
 
 
 def generate_header(scenarios) -> str:

@@ -185,6 +185,18 @@ __global__ void __launch_bounds__(kGenBlock, CRL_GEN_MINB) gen_solve_kernel(GenP
 
 }  // namespace
 
+#ifdef CRL_USER_MODEL
+// the run-time compiled unit holds exactly one scenario: ids CRL_GEN_USER / CRL_GEN_USER_BARRIER
+#define CRL_GEN_DISPATCH(model, ...)                                                           \
+    switch (model) {                                                                           \
+        case CRL_GEN_USER: { using G = GenUser; __VA_ARGS__; } break;                          \
+        case CRL_GEN_USER_BARRIER: { using G = GenUserBarrier; __VA_ARGS__; } break;           \
+        default: break;                                                                        \
+    }
+
+bool gen_is_model(int model) { return model == CRL_GEN_USER || model == CRL_GEN_USER_BARRIER; }
+bool gen_is_barrier(int model) { return model == CRL_GEN_USER_BARRIER; }
+#else
 #define CRL_GEN_DISPATCH(model, ...)                                                           \
     switch (model) {                                                                           \
         case CRL_GEN_CART_POLE_1: { using G = GenCartPoleSwingUp1; __VA_ARGS__; } break;       \
@@ -200,6 +212,7 @@ __global__ void __launch_bounds__(kGenBlock, CRL_GEN_MINB) gen_solve_kernel(GenP
 
 bool gen_is_model(int model) { return model >= CRL_GEN_CART_POLE_1 && model <= CRL_GEN_CAR_PARKING_BARRIER; }
 bool gen_is_barrier(int model) { return model >= CRL_GEN_CART_POLE_1_BARRIER && model <= CRL_GEN_CAR_PARKING_BARRIER; }
+#endif
 
 int gen_dims(int model, int* n, int* m, int* p) {
     if (!gen_is_model(model)) return -1;

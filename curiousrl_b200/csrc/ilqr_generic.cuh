@@ -16,20 +16,29 @@
 #pragma once
 
 #include "ilqr_core.cuh"
+#ifdef CRL_USER_MODEL
+// run-time compiled model (curiousrl_b200/jit.py): the generated header of ONE scenario, structs GenUser / GenUserBarrier
+#include CRL_USER_HEADER
+#else
 #include "ilqr_generated.cuh"
+#endif
+
+#ifndef CRL_GEN_MAX_D
+#define CRL_GEN_MAX_D 8          // components (n + m) a GenBox holds; the run-time compiled unit raises it to 16
+#endif
 
 namespace crl {
 
 // The box `constr` of a problem, component by component (states first).  The generated models carry the scenario's
 // default box (G::lo / G::hi); a caller may pass another one (e.g. is_with_constraints=False: all +-inf).
 struct GenBox {
-    double lo[8], hi[8];
+    double lo[CRL_GEN_MAX_D], hi[CRL_GEN_MAX_D];
 };
 template <class G>
 CRL_HD GenBox gen_default_box() {
-    static_assert(G::D <= 8, "GenBox holds up to 8 components");
+    static_assert(G::D <= CRL_GEN_MAX_D, "GenBox holds up to CRL_GEN_MAX_D components");
     GenBox b;
-    for (int i = 0; i < 8; ++i) { b.lo[i] = i < G::D ? G::lo(i) : 0.0; b.hi[i] = i < G::D ? G::hi(i) : 0.0; }
+    for (int i = 0; i < CRL_GEN_MAX_D; ++i) { b.lo[i] = i < G::D ? G::lo(i) : 0.0; b.hi[i] = i < G::D ? G::hi(i) : 0.0; }
     return b;
 }
 

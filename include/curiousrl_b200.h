@@ -56,7 +56,12 @@ enum crl_model {              /* scenario.name -> precompiled device model      
     CRL_GEN_CART_POLE_1_BARRIER = 10,
     CRL_GEN_CART_POLE_2_BARRIER = 11,
     CRL_GEN_VEHICLE_TRACKING_BARRIER = 12,
-    CRL_GEN_CAR_PARKING_BARRIER = 13
+    CRL_GEN_CAR_PARKING_BARRIER = 13,
+    /* A scenario compiled at run time (curiousrl_b200/jit.py: the same generator, nvcc at `init`, a library of its own
+       that exports this ABI for exactly these two ids - the way BasiciLQR.init takes ANY DynamicModelWrapper,
+       basic_ilqr.py:50-66).  The main library answers CRL_ERR_UNSUPPORTED_MODEL for them.              */
+    CRL_GEN_USER = 100,
+    CRL_GEN_USER_BARRIER = 101
 };
 enum crl_dtype { CRL_F64 = 0, CRL_F32 = 1 };
 enum crl_line_search { CRL_LS_VANILLA = 0, CRL_LS_FEASIBILITY = 1, CRL_LS_NONE = 2 }; /* ilqr_wrapper.py:74-146 */

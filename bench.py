@@ -309,6 +309,37 @@ def workload_config(args, n_gpus):
                      "a 512 MB buffer is overwritten between timed steps"}
 
 
+def measure_nn_jacobian(dev, trajectories=4096, horizon=100):
+    """SURVEY 8(f) N4, the one tensor-core kernel of the product: value + Jacobian of the learned dynamics
+    (`LargeNetwork`, random weights in eval mode) at trajectories x horizon rows in one crl_mlp_jacobian call."""
+    import torch
+    from curiousrl_b200.algorithm.ilqr_solver.nn_ilqr import FoldedMLP, LargeNetwork
+    n, d = 8, 11
+    torch.manual_seed(0)
+    f = FoldedMLP(LargeNetwork(d, n).to(dev).eval(), dev)
+    S = trajectories * horizon
+    x = torch.randn(S, d, device=dev)
+    f.jacobian(x)
+    torch.cuda.synchronize()
+    steps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        f.jacobian(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    flops = 2.0 * S * (d * f.h1 + f.h1 * f.h2 + n * f.h2 + n * f.h2 * f.h1 + n * f.h1 * d)
+    peak = 1100.0                                          # TFLOP/s: dense TF32 tensor peak of a B200 (B200_PROFILING.md)
+    return {"workload": "NNiLQR learned-dynamics Jacobian (nn_ilqr.py:265-274): LargeNetwork 11-800-400-8, %d trajectories x "
+                        "T=%d = %d rows per call, tcgen05 kind::tf32" % (trajectories, horizon, S),
+            "model": "LargeNetwork", "rows": S, "dtype": "tf32 in / f32 accumulate", "steps": steps, "warmup": 1, "ms_per_step": ms,
+            "value": S / (ms * 1e-3), "unit": "rows/s",
+            "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                         "frac": flops / (ms * 1e-3) / 1e12 / peak, "peak_source": "nominal dense TF32 (B200_PROFILING.md)"},
+            "timing": "CUDA events on the launch stream"}
+
+
 # ----------------------------------------------------------------------------- B200 arm
 def run_b200(args):
     import torch
@@ -493,6 +524,8 @@ def run_b200(args):
         else:
             also.append(measure("BASELINE config 4 shard size: ThreeLink 131,072 per GPU (x %d GPUs = %d), T=100, FP64, to "
                                 "convergence, terminal gather included" % (world, 131072 * world), MODEL, 131072, 100, 2))
+        if world == 1:
+            also.append(measure_nn_jacobian(dev))
 
     if rank != 0:
         if world > 1:

@@ -349,9 +349,47 @@ class BasiciLQR(iLQRWrapper):
                 raise Exception('Scenario "%s": obj_fun differs from the device model' % scenario.name)
 
     # ------------------------------------------------------------------ solve (B = 1, reference semantics)
-    def solve(self):
+    def _solve_recording(self):
+        """`solve()` with one record per iteration in the logger's JSON channel, as the reference writes them
+        (basic_ilqr.py:81-95: `logger.save_to_json(trajectory=...)` inside the loop, replayed by
+        `read_from_json(folder, no_iter)` / `scenario.play(folder, no_iter)`): the loop runs on the host with one
+        backward and one forward-pass call per iteration.  Same device functions as the fused kernel, hence the same
+        numbers (tests/test_gpu_solve_parity.py::test_recorded_solve_equals_the_fused_one)."""
+        dev = self._dev
+        start = _time.time()
+        x0 = np.asarray(self._dynamic_model._init_state, dtype=np.float64).reshape(1, dev.n)
+        u0 = np.asarray(self._dynamic_model._init_action, dtype=np.float64)
+        prm = self._params_for(1)
+        X, J0 = dev.rollout(x0, prm, u0 if u0.any() else None)
+        logger.info("[+ +] Initial Obj.Val.: %.5e" % float(J0.item()))
+        J_last = torch.tensor([self._obj_fun_value_last], dtype=torch.float64, device=dev.device)
+        opts = self._opts()
+        for i in range(self._max_iter):
+            K, k = dev.backward(X, prm)
+            X, J_last, _aidx, stop = dev.forward_pass(opts, X, K, k, J_last, prm)
+            self._trajectory = _np(X)[0][:, :, None]
+            logger.info("[+ +] Iter.No.%3d   Obj.Val.:%.5e" % (i, float(J_last.item())))
+            logger.save_to_json(trajectory=self._trajectory.tolist())
+            if bool(stop.item()) and self._is_check_stop:
+                break
+        self._obj_fun_value_last = float(J_last.item())
+        self.last_result = None
+        logger.info("[+ +] Completed! All Time:%.5e" % (_time.time() - start))
+
+    def solve(self, record_iterations=None):
         """Solve the scenario's problem.  Returns None; results are left in `_trajectory`,
-        `get_obj_fun_value()` and the logger's JSON channel, as in basic_ilqr.py:68-97."""
+        `get_obj_fun_value()` and the logger's JSON channel, as in basic_ilqr.py:68-97.
+
+        record_iterations: True = one JSON record per iteration like the reference (host loop, two kernels per
+        iteration); False = the whole solve in one kernel and one record for the final trajectory.  Default: True when the
+        logger saves its records to disk (`logger.set_is_save_json(True)` - the per-iteration replay is what those
+        files are for), False otherwise (in memory only the last record can be read back anyway)."""
+        if record_iterations is None:
+            record_iterations = bool(logger.IS_SAVE_JSON)
+        if record_iterations:
+            if self._dev.dtype_name != "float64":
+                raise ValueError("record_iterations needs dtype='float64'")
+            return self._solve_recording()
         dev = self._dev
         start = _time.time()
         x0 = np.asarray(self._dynamic_model._init_state, dtype=np.float64).reshape(1, dev.n)

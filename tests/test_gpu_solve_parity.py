@@ -285,3 +285,29 @@ def test_scheduling_paths_at_tiny_horizons(model, T):
         res = make_algo(model, T, verify=False, max_iter=30, **kw).solve_batch(x0, tgt, trace=True)
         for f in ("iterations", "converged", "obj_fun_value", "trajectory", "alpha_trace"):
             assert torch.equal(getattr(res, f), getattr(ref, f)), "%s differs with %s at T=%d" % (f, kw, T)
+
+
+def test_recorded_solve_equals_the_fused_one(golden):
+    """`logger.set_is_save_json(True)`: one record per iteration like the reference (basic_ilqr.py:93), replayable with
+    `read_from_json(folder, no_iter)` (Logger.py:82-99) - and the same final numbers, bit for bit, as the fused solve."""
+    from curiousrl_b200 import logger
+    g = golden("ThreeLink_T100")
+    fused = make_algo("ThreeLinkPlanarManipulator", 100)
+    fused.solve()
+    iters = int(fused.last_result.iterations.item())
+    assert iters == int(g["default_iters"])
+    logger.set_folder_name("test_recorded_solve", remove_existing_folder=True).set_is_use_logger(True).set_is_save_json(True)
+    try:
+        rec = make_algo("ThreeLinkPlanarManipulator", 100)
+        rec.solve()
+        assert rec.get_obj_fun_value() == fused.get_obj_fun_value()
+        assert np.array_equal(rec._trajectory, fused._trajectory)
+        last = np.asarray(logger.read_from_json("test_recorded_solve", -1)["trajectory"])
+        assert np.array_equal(last, fused._trajectory)
+        first = np.asarray(logger.read_from_json("test_recorded_solve", 0)["trajectory"])
+        assert first.shape == (100, 11, 1) and not np.array_equal(first, last)
+        assert np.array_equal(np.asarray(logger.read_from_json("test_recorded_solve", iters - 1)["trajectory"]), last)
+        with pytest.raises(Exception):
+            logger.read_from_json("test_recorded_solve", iters)
+    finally:
+        logger.set_is_save_json(False).set_is_use_logger(False)

@@ -16,12 +16,31 @@ def _stub_namespace():
     from curiousrl_b200 import build
     text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
-    code = [b for b in blocks if "def solve_on_b200" in b or "def log_barrier_on_b200" in b]
-    assert len(code) == 2
+    code = [b for b in blocks if "def solve_on_b200" in b or "def log_barrier_on_b200" in b or "def jacobians_on_b200" in b]
+    assert len(code) == 3
     ns = {}
     exec(code[0].replace('ctypes.CDLL("libcuriousrl_b200.so")', "ctypes.CDLL(%r)" % build.LIB_PATH), ns)
     exec(code[1], ns)
+    exec(code[2], ns)
     return ns
+
+
+def test_jacobian_stub_equals_the_package():
+    """`jacobians_on_b200`: the override of NNiLQRDynamicModel.eval_grad_dynamic_model shown in the guide, on the
+    reference-shaped network, against the package's own `NNiLQRDynamicModel` - the same kernels, the same bits."""
+    from curiousrl_b200.algorithm.ilqr_solver import LargeNetwork, NNiLQRDynamicModel
+    ns = _stub_namespace()
+    torch.manual_seed(1)
+    net = LargeNetwork(11, 8).cuda()
+    net.train()
+    with torch.no_grad():
+        net(torch.randn(256, 11, device="cuda"))
+    net.eval()
+    rng = np.random.default_rng(0)
+    traj = rng.normal(size=(100, 11, 1))
+    F = ns["jacobians_on_b200"](net, traj)
+    model = NNiLQRDynamicModel(net, np.zeros((8, 1)), np.zeros((100, 3, 1)))
+    assert F.shape == (100, 8, 11) and np.array_equal(F, model.eval_grad_dynamic_model(traj))
 
 
 def test_stubs_of_the_integration_guide_run_and_agree_with_the_package():

@@ -429,6 +429,28 @@ __host__ __device__ constexpr long long lane_tiles_reals(int T) {
     return (long long)T * 32 * (2 * Mdl::D + Mdl::M * Mdl::NS + Mdl::M);
 }
 
+// Warp-cooperative copy of one trajectory between layouts: element e of the destination comes from src_at(e).  The loads
+// of kCopyBatch elements per lane are issued before any of them is stored: written as `dst[e] = src[...]` the compiler must
+// assume the two arrays alias and waits for every load (a DRAM access from a tile that left the L2 long ago) before the
+// next one - 35 serialised round trips per trajectory (measured: the retire phase was 14 % of lane mode).
+constexpr int kCopyBatch = 8;
+template <class R, class SrcAt>
+__device__ __forceinline__ void warp_copy_elems(R* dst, int n, int lane, SrcAt src_at) {
+    for (int e0 = lane; e0 < n; e0 += 32 * kCopyBatch) {
+        R v[kCopyBatch];
+#pragma unroll
+        for (int j = 0; j < kCopyBatch; ++j) {
+            const int e = e0 + 32 * j;
+            if (e < n) v[j] = *src_at(e);
+        }
+#pragma unroll
+        for (int j = 0; j < kCopyBatch; ++j) {
+            const int e = e0 + 32 * j;
+            if (e < n) dst[e] = v[j];
+        }
+    }
+}
+
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
     return *reinterpret_cast<const volatile unsigned long long*>(p);
 }
@@ -749,8 +771,18 @@ struct StragglerSource {
             J[q] = __ldcg(&qe->J_last);
             it[q] = __ldcg(&qe->it);
             const int n = a.pb.T * Mdl::D;
-            for (int e = lane; e < n; e += 32)
-                dst[q][(size_t)(e / Mdl::D) * coop_rs<Mdl, NT>() + e % Mdl::D] = __ldcg(src + (size_t)e * 32);
+            R* const dq = dst[q];
+            for (int e0 = lane; e0 < n; e0 += 32 * kCopyBatch) {        // loads first (see warp_copy_elems)
+                R v[kCopyBatch];
+#pragma unroll
+                for (int j = 0; j < kCopyBatch; ++j)
+                    if (e0 + 32 * j < n) v[j] = __ldcg(src + (size_t)(e0 + 32 * j) * 32);
+#pragma unroll
+                for (int j = 0; j < kCopyBatch; ++j) {
+                    const int e = e0 + 32 * j;
+                    if (e < n) dq[(size_t)(e / Mdl::D) * coop_rs<Mdl, NT>() + e % Mdl::D] = v[j];
+                }
+            }
             claim[q] = -1;
             got |= 1u << q;
         }
@@ -979,7 +1011,7 @@ __device__ void coop_engine(const SolveArgs<R>& a, Source& src, R* xscr, R* gscr
                 if (a.X_out) {
                     const R* from = xscr + (size_t)(2 * q + s_buf[q]) * BUF + s_col[q] * DP;
                     R* to = a.X_out + s_traj[q] * TD;
-                    for (int e = lane; e < T * D; e += 32) to[e] = from[(size_t)(e / D) * RS + e % D];
+                    warp_copy_elems<R>(to, T * D, lane, [from](int e) { return from + (size_t)(e / D) * RS + e % D; });
                     __syncwarp();                               // the buffers are reused by the slot's next trajectory
                 }
                 s_traj[q] = -1;
@@ -1347,9 +1379,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) solve_kernel(SolveArgs<R> a)
                 const bool acc_o = __shfl_sync(kFull, (int)accepted, owner) != 0;
                 const R* col = (acc_o ? Xn.base : Xc.base) - lane + owner;
                 R* dst = a.X_out + tj * T * D;
-                const int n = T * D;
-#pragma unroll 4
-                for (int e = lane; e < n; e += 32) dst[e] = col[(size_t)e * 32];
+                warp_copy_elems<R>(dst, T * D, lane, [col](int e) { return col + (size_t)e * 32; });
             }
         }
         // lanes that go on without an accepted step carry their trajectory into the other

@@ -60,7 +60,8 @@ def test_solver_constructor_and_accessors_without_gpu():
 
 def test_unsupported_scenario_raises_instead_of_falling_back():
     from curiousrl_b200.algorithm.ilqr_solver import DeviceModel
-    with pytest.raises(Exception, match="no device model"):
+    # a name without a precompiled model and no scenario object to compile one from (curiousrl_b200/jit.py): refused
+    with pytest.raises(Exception, match="no precompiled device model"):
         DeviceModel("TwoWheeledRobot", 100, -1.0, 1.0)
 
 

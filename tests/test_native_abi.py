@@ -127,3 +127,35 @@ def test_product_package_never_imports_the_oracle():
                 text = open(os.path.join(base, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "hostsim" not in text or f == "ilqr_common.cuh", f
+
+
+def test_learned_dynamics_entry_points_validate_before_any_cuda_call():
+    """crl_mlp_jacobian / crl_smooth_time (NNiLQR): sizes outside what the kernels are written for, missing
+    buffers, a workspace that is too small or misaligned and host pointers are all refused with a status - no launch."""
+    from curiousrl_b200 import _native
+    lib = _native.load()
+    vp = ctypes.c_void_p
+    raw = np.zeros(4096 + 64, dtype=np.float32)
+    off = (-raw.ctypes.data % 256) // 4                                   # a 256-byte aligned view
+    buf = raw[off:off + 4096]
+    p = buf.ctypes.data_as(vp)
+    need = lib.crl_mlp_jacobian_workspace_bytes(11, 800, 416, 8, 100, 1)
+    assert need > 0 and lib.crl_mlp_jacobian_workspace_bytes(11, 800, 416, 8, 100, 0) > need        # impl 0 keeps its activations
+    assert lib.crl_mlp_jacobian_workspace_bytes(11, 0, 416, 8, 100, 1) == 0
+
+    def call(d=11, h1=800, h2=416, n=8, S=100, ws=p, ws_bytes=1 << 30, impl=1, x=p):
+        return lib.crl_mlp_jacobian(d, h1, h2, n, S, x, p, p, p, p, p, p, p, p, p, ws, ws_bytes, impl, None)
+
+    assert call(S=0) == 0                                                 # nothing to do
+    for bad in (dict(d=17), dict(d=0), dict(n=17), dict(h1=801), dict(h2=400), dict(h2=544), dict(h1=16), dict(S=-1), dict(impl=2)):
+        assert call(**bad) == -1, bad                                     # CRL_ERR_BAD_ARGUMENT
+    assert call(x=None) == -1 and call(ws=None) == -1
+    assert call(ws_bytes=16) == -3                                        # CRL_ERR_WORKSPACE_TOO_SMALL
+    assert call(ws=vp(buf.ctypes.data + 4)) == -1                         # workspace must be 256-byte aligned
+    assert call() < 0                                                     # host pointers never reach a kernel
+    g = np.zeros((4, 4))
+    gp = g.ctypes.data_as(vp)
+    assert lib.crl_smooth_time(0, 4, 3, gp, gp, gp, None) == 0
+    assert lib.crl_smooth_time(1, 0, 3, gp, gp, gp, None) == -1 and lib.crl_smooth_time(1, 4, 3, gp, gp, gp, None) == -1   # in == out
+    out = np.zeros((4, 3))
+    assert lib.crl_smooth_time(1, 4, 3, gp, g.ctypes.data_as(vp), out.ctypes.data_as(vp), None) < 0          # host pointers

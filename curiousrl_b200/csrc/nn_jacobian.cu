@@ -446,12 +446,9 @@ mlp_jacobian_kernel(MlpDims dm, const float* __restrict__ w1, const float* __res
                 for (int j = 0; j < kMaxD; ++j) acc[j] = 0.0f;
                 if (p.ti + 1 < my_tiles) load_masks(tile + gridDim.x, slot ^ 1);   // read from the next tile's first block on
             }
-            if (b + 1 < total) {
-                issue_b(q);
-                q.next(nchunks, nkb);
-            }
             // A block: row (s, r) of G2 = W3[r, :] masked by m2[s, :], 32 hidden units of layer 2 (the stage is free: its
-            // previous use was waited for when this block's B was issued)
+            // previous use was waited for when this block's B was issued).  Formed BEFORE the next block's cp.async's are
+            // issued: shared-memory loads queue behind them in the load/store unit.
             float4* Ab = Ablk + p.stage * (8 * 128);
             const uint32_t bits = valid ? my_m2[p.kb] : 0u;
 #pragma unroll
@@ -461,11 +458,14 @@ mlp_jacobian_kernel(MlpDims dm, const float* __restrict__ w1, const float* __res
                 Ab[c * 128 + row] = make_float4((bits >> (c * 4 + 0)) & 1u ? w.x : 0.0f, (bits >> (c * 4 + 1)) & 1u ? w.y : 0.0f,
                                                 (bits >> (c * 4 + 2)) & 1u ? w.z : 0.0f, (bits >> (c * 4 + 3)) & 1u ? w.w : 0.0f);
             }
-            if (b + 1 < total) asm volatile("cp.async.wait_group 1;" ::: "memory");
-            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");             // B of THIS block (issued one block ago)
             proxy_fence();
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(bar_full + p.stage);
+            if (b + 1 < total) {                                              // fetch the next block's B while this one is multiplied
+                issue_b(q);
+                q.next(nchunks, nkb);
+            }
             // the epilogue of the previous chunk, one pair of groups per block (all that is left at the chunk's last block)
             if (pend_chunk >= 0) {
                 if (pend_group == 0) drain_begin(pend_chunk);

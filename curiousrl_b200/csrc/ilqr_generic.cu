@@ -136,11 +136,135 @@ constexpr long long gen_tile_reals(int T) {
     return (long long)T * 32 * (2 * G::D + G::M * G::N + G::M);
 }
 
+// The solves of the 32 trajectories of a warp, iteration by iteration in lock step (same results as gen_solve_one per
+// trajectory, bit for bit: every candidate of the line search is gen_rollout_closed's arithmetic).  What it adds is the
+// LINE-SEARCH HELPERS: a lane whose trajectory has finished, or has its step for this iteration, would idle while the
+// warp runs one pass per step size for its slowest lane - and every trajectory's LAST iteration rejects all
+// max_line_search step sizes (ncu of the per-thread kernel on VehicleTracking: 14.3 of 32 lanes active in the rollouts).
+// Here the idle lanes evaluate the NEXT step sizes of the trajectories that are still searching, cost only, reading the
+// owner's columns of X, K, k (same sectors: no extra traffic): with n_pend searching lanes and n_help idle ones a pass
+// covers 1 + n_help / n_pend step sizes per trajectory.  If a helper's step size is the first improving one the owner
+// repeats that rollout with stores (one more pass for the warp, instead of one per skipped step size).
+template <class G>
+__device__ void gen_solve_warp(bool valid, const double* x0, const double* U, int su_t, GenParams prm, int T, const GenOpts& op,
+                               double J_init, View<double, G::D, 32> Xa, View<double, G::D, 32> Xb,
+                               View<double, G::M * G::N, 32> K, View<double, G::M, 32> k, double* J_out, int* iters_out,
+                               uint8_t* conv_out, bool* final_in_a, double* J_trace, signed char* alpha_trace, int n_stage,
+                               long long stage_stride, int* stage_iters) {
+    constexpr unsigned kAll = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    if (valid) gen_rollout_open<G>(x0, U, su_t, prm, T, Xa);
+    bool active = valid, in_a = true, stopped = false;
+    double J_last = J_init;
+    const int tries = op.ls_method == 2 /* CRL_LS_NONE */ ? 1 : op.max_ls;
+    int s = 0, it = 0, total = 0;
+    GenParams ps = prm;
+    while (__any_sync(kAll, active)) {
+        const View<double, G::D, 32> Xc = in_a ? Xa : Xb, Xn = in_a ? Xb : Xa;
+        if (active) gen_backward<G>(Xc, ps, T, K, k, it == 0);
+        __syncwarp();                                           // the helpers read the owner's K, k (and its X of the last pass)
+        bool accepted = false, replay = false;
+        double J_new = J_last, alpha = 1.0, alpha_taken = 1.0;
+        int taken = -1, a0 = 0;
+        while (a0 < tries) {
+            const bool pending = active && !accepted;
+            const unsigned pm = __ballot_sync(kAll, pending);
+            if (pm == 0u) break;
+            const int n_pend = __popc(pm);
+            int per = (32 - n_pend) / n_pend;                   // helpers per searching trajectory
+            if (per > tries - a0 - 1) per = tries - a0 - 1;
+            const unsigned hm = ~pm;
+            const int rank_p = __popc(pm & lt), rank_h = __popc(hm & lt);
+            const bool helper = !pending && rank_h < per * n_pend;
+            const int owner = helper ? (int)__fns(pm, 0, rank_h % n_pend + 1) : lane;
+            const int j = helper ? 1 + rank_h / n_pend : 0;     // this lane's step size: index a0 + j
+            // the owner's problem
+            const double Jl_o = __shfl_sync(kAll, J_last, owner);
+            const bool in_a_o = __shfl_sync(kAll, (int)in_a, owner) != 0;
+            GenParams ps_o = ps;
+            ps_o.ptr = (const double*)(uintptr_t)__shfl_sync(kAll, (unsigned long long)(uintptr_t)ps.ptr, owner);
+            double Jt = 0.0;
+            bool ok = false;
+            if (pending || helper) {
+                double al = alpha;
+                for (int i = 0; i < j; ++i) al = al * op.gamma;
+                const int shift = owner - lane;
+                const View<double, G::D, 32> Xc_o{(in_a_o ? Xa.base : Xb.base) + shift};
+                const View<double, G::M * G::N, 32> K_o{K.base + shift};
+                const View<double, G::M, 32> k_o{k.base + shift};
+                Jt = gen_rollout_closed<G>(Xc_o, K_o, k_o, al, ps_o, T, Xn, pending);
+                ok = op.ls_method == 2 || ls_accept(Jt, Jl_o, op.ls_method == 1);
+            }
+            const unsigned okm = __ballot_sync(kAll, ok);
+            int w = -1, src = lane;
+            if (pending) {
+                if ((okm >> lane) & 1u) {
+                    w = 0;
+                } else {
+                    for (int jj = 0; jj < per && w < 0; ++jj) {
+                        const unsigned hl = __fns(hm, 0, rank_p + jj * n_pend + 1);
+                        if (hl < 32u && ((okm >> hl) & 1u)) { w = jj + 1; src = (int)hl; }
+                    }
+                }
+            }
+            const double Jw = __shfl_sync(kAll, Jt, src);
+            if (pending && w >= 0) {
+                accepted = true;
+                taken = a0 + w;
+                J_new = Jw;
+                if (w > 0) {
+                    replay = true;
+                    double al = alpha;
+                    for (int i = 0; i < w; ++i) al = al * op.gamma;
+                    alpha_taken = al;
+                }
+            }
+            for (int i = 0; i < 1 + per; ++i) alpha = alpha * op.gamma;
+            a0 += 1 + per;
+        }
+        if (__any_sync(kAll, replay)) {
+            if (replay) gen_rollout_closed<G>(Xc, K, k, alpha_taken, ps, T, Xn, true);
+        }
+        if (active) {
+            const bool stop = stop_test(J_new, J_last, op.criterion, op.stop_method == 0);
+            J_last = J_new;
+            if (accepted) in_a = !in_a;
+            if (J_trace) J_trace[it] = J_new;
+            if (alpha_trace) alpha_trace[it] = (signed char)taken;
+            ++it;
+            if (stop && op.check_stop) stopped = true;
+            if (stopped || it >= op.max_iter) {               // this inner loop is over (log_barrier_ilqr.py:121-146)
+                if (stage_iters) stage_iters[s] = it;
+                total += it;
+                ++s;
+                if (s < n_stage) {
+                    ps.ptr = prm.ptr + (size_t)s * stage_stride;
+                    if (stopped) J_last = (double)INFINITY;
+                    it = 0;
+                    stopped = false;
+                } else {
+                    active = false;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (valid) {
+        *J_out = J_last;
+        *iters_out = total;
+        *conv_out = stopped ? (uint8_t)1 : (uint8_t)0;
+    }
+    *final_in_a = in_a;
+}
+
 #ifndef CRL_GEN_MINB
 #define CRL_GEN_MINB 4
 #endif
 // 4 resident CTAs per SM (128 registers per thread): 75,776 resident threads, so the benchmark batch of 65,536 is one wave
-template <class G>
+// WARPSYNC = true: gen_solve_warp (lock step + line-search helpers, the default); false: gen_solve_one per thread
+// (opts->reserved == 2, "warps free-running": the checker of the other one)
+template <class G, bool WARPSYNC>
 __global__ void __launch_bounds__(kGenBlock, CRL_GEN_MINB) gen_solve_kernel(GenProblemDev pb, GenOpts op, const double* x0,
                                                               const double* u0, long long u0_sb, const double* J_init,
                                                               double* X_out, double* J_out, int* iters_out,
@@ -156,7 +280,15 @@ __global__ void __launch_bounds__(kGenBlock, CRL_GEN_MINB) gen_solve_kernel(GenP
     const View<double, M * N, 32> Kv{tile + (size_t)2 * T * D * 32};
     const View<double, M, 32> kv{tile + (size_t)2 * T * D * 32 + (size_t)T * M * N * 32};
     bool in_a = true;
-    if (b < pb.B) {
+    if constexpr (WARPSYNC) {
+        const bool valid = b < pb.B;
+        const long long bb = valid ? b : 0;
+        gen_solve_warp<G>(valid, x0 + bb * N, u0 ? u0 + bb * u0_sb : nullptr, M, pb.prm(bb), T, op,
+                          J_init ? J_init[bb] : (double)INFINITY, Xa, Xb, Kv, kv, J_out + bb, iters_out + bb,
+                          conv_out + bb, &in_a, J_trace ? J_trace + bb * op.max_iter : nullptr,
+                          alpha_trace ? (signed char*)alpha_trace + bb * op.max_iter : nullptr, n_stage, stage_stride,
+                          stage_iters ? stage_iters + bb * n_stage : nullptr);
+    } else if (b < pb.B) {
         double J = 0.0;
         int iters = 0, conv = 0;
         gen_solve_one<G>(x0 + b * N, u0 ? u0 + b * u0_sb : nullptr, M, pb.prm(b), T, op,
@@ -178,7 +310,17 @@ __global__ void __launch_bounds__(kGenBlock, CRL_GEN_MINB) gen_solve_kernel(GenP
             const bool a_o = __shfl_sync(0xffffffffu, (int)in_a, owner) != 0;
             const double* col = (a_o ? Xa.base : Xb.base) - lane + owner;
             double* dst = X_out + bo * T * D;
-            for (int e = lane; e < T * D; e += 32) dst[e] = col[(size_t)e * 32];
+            // 8 loads in flight before the stores (one load per store is one DRAM round trip per element: the compiler
+            // must assume that the tile and X_out alias)
+            for (int e0 = lane; e0 < T * D; e0 += 32 * 8) {
+                double v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (e0 + 32 * j < T * D) v[j] = col[(size_t)(e0 + 32 * j) * 32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (e0 + 32 * j < T * D) dst[e0 + 32 * j] = v[j];
+            }
         }
     }
 }
@@ -269,11 +411,19 @@ int gen_launch_solve(const crl_problem_t* prob, const crl_solver_opts_t* opts, c
                      int32_t* stage_iters) {
     // whole warps: the result write-out is a warp-cooperative loop
     const unsigned grid = blocks(((prob->batch + 31) / 32) * 32);
-    CRL_GEN_DISPATCH(prob->model, (gen_solve_kernel<G><<<grid, kGenBlock, 0, s>>>(
-                                      to_gen(prob), to_gen(opts), x0, u0, u0_sb, J_init, X, J, iters, converged, J_trace,
-                                      alpha_trace, (double*)workspace, n_stage,
-                                      prob->params_stride_t ? (long long)prob->horizon * G::P : (long long)G::P,
-                                      stage_iters)));
+    if (opts->reserved == 2) {
+        CRL_GEN_DISPATCH(prob->model, (gen_solve_kernel<G, false><<<grid, kGenBlock, 0, s>>>(
+                                          to_gen(prob), to_gen(opts), x0, u0, u0_sb, J_init, X, J, iters, converged, J_trace,
+                                          alpha_trace, (double*)workspace, n_stage,
+                                          prob->params_stride_t ? (long long)prob->horizon * G::P : (long long)G::P,
+                                          stage_iters)));
+    } else {
+        CRL_GEN_DISPATCH(prob->model, (gen_solve_kernel<G, true><<<grid, kGenBlock, 0, s>>>(
+                                          to_gen(prob), to_gen(opts), x0, u0, u0_sb, J_init, X, J, iters, converged, J_trace,
+                                          alpha_trace, (double*)workspace, n_stage,
+                                          prob->params_stride_t ? (long long)prob->horizon * G::P : (long long)G::P,
+                                          stage_iters)));
+    }
     return (int)cudaGetLastError();
 }
 

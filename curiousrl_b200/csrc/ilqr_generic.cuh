@@ -143,8 +143,9 @@ CRL_HD void gen_backward(XV X, GenParams prm, int T, KV K, SV k, bool first = fa
 }
 
 // Closed-loop rollout for one step size; writes Xn, returns its cost.
+// `store = false`: cost only (the line-search helpers of gen_solve_warp); same arithmetic, nothing written.
 template <class G, class XV, class KV, class SV, class XW>
-CRL_HD double gen_rollout_closed(XV X, KV K, SV k, double alpha, GenParams prm, int T, XW Xn) {
+CRL_HD double gen_rollout_closed(XV X, KV K, SV k, double alpha, GenParams prm, int T, XW Xn, bool store = true) {
     constexpr int N = G::N, M = G::M, D = G::D;
     double xu[D], xo[D], xn[N], p[G::P];
     {
@@ -183,8 +184,10 @@ CRL_HD double gen_rollout_closed(XV X, KV K, SV k, double alpha, GenParams prm, 
         } else {
             if (T > 1) { for (int a = 0; a < M; ++a) xu[N + a] = 0.0; }        // last action stays 0 (:133)
         }
-        double* rw = Xn.row(t);
-        for (int i = 0; i < D; ++i) Xn.st(rw, i, xu[i]);
+        if (store) {
+            double* rw = Xn.row(t);
+            for (int i = 0; i < D; ++i) Xn.st(rw, i, xu[i]);
+        }
         prm.load(t, p);
         J = J + G::cost(xu, p);
         if (!last) {

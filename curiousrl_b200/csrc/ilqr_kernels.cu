@@ -451,6 +451,34 @@ __device__ __forceinline__ void warp_copy_elems(R* dst, int n, int lane, SrcAt s
     }
 }
 
+// Copies one lane's trajectory (column of a warp tile, elements 32 reals apart) into the other tile.  A function of its
+// own ON PURPOSE: it runs only for trajectories that go on without an accepted step (is_check_stop = False), and inlined
+// into the lane loop its registers and code moved the allocation of the loop's hot passes (the converging solve of
+// 1,048,576 problems got 4 % slower).  kCarryRows rows are loaded before any of them is stored: written as one load per
+// store the compiler must assume that the two tiles alias and every element waits for a DRAM round trip of its own
+// (ncu, fixed-work run: 30 % of the kernel's stall samples sat on these stores).
+template <class R, int D>
+__device__ __noinline__ void carry_tile_column(const R* src, R* dst, int T) {
+    constexpr int kCarryRows = 4;
+    for (int t0 = 0; t0 < T; t0 += kCarryRows) {
+        R v[kCarryRows][D];
+#pragma unroll
+        for (int j = 0; j < kCarryRows; ++j) {
+            if (t0 + j < T) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) v[j][i] = src[((size_t)(t0 + j) * D + i) * 32];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kCarryRows; ++j) {
+            if (t0 + j < T) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) dst[((size_t)(t0 + j) * D + i) * 32] = v[j][i];
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
     return *reinterpret_cast<const volatile unsigned long long*>(p);
 }
@@ -1386,15 +1414,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) solve_kernel(SolveArgs<R> a)
         // buffer so that `cur` can flip for the whole warp
         const bool carry = active && !finished && !accepted;
         if (__any_sync(kFull, carry)) {
-            if (carry) {
-#pragma unroll 8
-                for (int t = 0; t < T; ++t) {
-                    const R* src = Xc.row(t);
-                    R* dst = Xn.row(t);
-#pragma unroll
-                    for (int i = 0; i < D; ++i) Xn.st(dst, i, Xc.ld(src, i));
-                }
-            }
+            if (carry) carry_tile_column<R, D>(Xc.base, Xn.base, T);
         }
         if (finished) traj = -1;
         cur ^= 1;
@@ -1484,7 +1504,7 @@ static int check_problem(const crl_problem_t* p) {
 static int check_opts(const crl_solver_opts_t* o) {
     if (!o) return CRL_ERR_BAD_ARGUMENT;
     if (o->max_iter < 0 || o->max_line_search < 0 || o->reserved2 != 0) return CRL_ERR_BAD_ARGUMENT;
-    if (o->reserved != 0 && o->reserved != 2 && o->reserved != 12 && (o->reserved < 20 || o->reserved > 23))
+    if (o->reserved != 0 && o->reserved != 2 && o->reserved != 12 && o->reserved != 13 && (o->reserved < 20 || o->reserved > 23))
         return CRL_ERR_BAD_ARGUMENT;             // a configuration that is not compiled in is rejected when the grid is sized
     if (o->line_search_method < CRL_LS_VANILLA || o->line_search_method > CRL_LS_NONE) return CRL_ERR_BAD_ARGUMENT;
     if (o->stopping_method < CRL_STOP_RELATIVE || o->stopping_method > CRL_STOP_VANILLA) return CRL_ERR_BAD_ARGUMENT;
@@ -1575,14 +1595,19 @@ static unsigned blocks_for(long long work) { return (unsigned)((work + kBlock - 
 
 // Launch configurations of the solve.  opts->reserved selects one (0 = default):
 //   2      : lane-per-trajectory kernel, 4 warps per CTA, 2 resident CTAs per SM, warps free-running
-//   12     : the same, warps of a CTA phase-locked (SYNC) - the default
+//   12     : the same, warps of a CTA phase-locked (SYNC)
+//   13     : 8 warps per CTA, 1 resident CTA per SM, phase-locked - the default: all eight warps of an SM run the same
+//            loop body at the same time, i.e. two warps per scheduler share the instruction stream (ncu of the
+//            1,048,576-problem solve: 0.9 `no_instruction` stall cycles per issued instruction - the loop bodies are
+//            11 - 14 KB against a ~6 KB L0 instruction cache).  Measured against 12, same box, bit-identical: ThreeLink
+//            65,536 -1 ... -5 %, 1,048,576 -0.5 ... -1.6 %, RoboticArm 262,144 x T = 200 -5 %, TwoLink -1 %.
 //   20, 21 : the cooperative engine as the whole solve (coop_solve_kernel, 4 trajectories per warp), 2 / 3
 //            resident CTAs per SM; 22, 23 (development builds, -DCRL_DEV_FAST): 2 / 8 trajectories per warp
 //            (element-per-lane / pair-group backward pass)
 // Every configuration produces the same results bit for bit.
 template <class R> struct SolveCfg;
-template <> struct SolveCfg<double> { static constexpr int kDefault = 12; };
-template <> struct SolveCfg<float> { static constexpr int kDefault = 12; };
+template <> struct SolveCfg<double> { static constexpr int kDefault = 13; };
+template <> struct SolveCfg<float> { static constexpr int kDefault = 13; };
 
 // A requested grid (opts->grid_blocks) is honoured up to the number of CTAs the device can hold at once.
 static int clamp_grid(int requested, int resident) { return requested > 0 && requested < resident ? requested : resident; }
@@ -1655,6 +1680,7 @@ struct CoopVariant {
     switch (v) {                                                                   \
         case 2: if constexpr (!Mdl::kBarrier) { using V = SolveVariant<Mdl, R, 4, 2, false>; __VA_ARGS__; } break;  \
         case 12: { using V = SolveVariant<Mdl, R, 4, 2, true>; __VA_ARGS__; } break;  \
+        case 13: { using V = SolveVariant<Mdl, R, 8, 1, true>; __VA_ARGS__; } break;  \
         case 20: { CRL_COOP_VARIANT(4, 2, kCoopNTFor<Mdl>, __VA_ARGS__) } break;         \
         case 21: { CRL_COOP_VARIANT(4, 3, kCoopNTFor<Mdl>, __VA_ARGS__) } break;         \
         case 22: if constexpr (!Mdl::kBarrier) { CRL_COOP_VARIANT(4, 2, 2, __VA_ARGS__) } break;   \
@@ -1666,6 +1692,7 @@ struct CoopVariant {
     switch (v) {                                                                   \
         case 2: if constexpr (!Mdl::kBarrier) { using V = SolveVariant<Mdl, R, 4, 2, false>; __VA_ARGS__; } break;  \
         case 12: { using V = SolveVariant<Mdl, R, 4, 2, true>; __VA_ARGS__; } break;  \
+        case 13: { using V = SolveVariant<Mdl, R, 8, 1, true>; __VA_ARGS__; } break;  \
         case 20: { CRL_COOP_VARIANT(4, 2, kCoopNTFor<Mdl>, __VA_ARGS__) } break;         \
         case 21: { CRL_COOP_VARIANT(4, 3, kCoopNTFor<Mdl>, __VA_ARGS__) } break;         \
         default: break;                                                            \

@@ -13,7 +13,9 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 MODELS = {"3l": ("ThreeLinkPlanarManipulator", 100), "2l": ("TwoLinkPlanarManipulator", 100),
-          "ra": ("RoboticArmTracking", 200), "ra100": ("RoboticArmTracking", 100)}
+          "ra": ("RoboticArmTracking", 200), "ra100": ("RoboticArmTracking", 100),
+          "veh": ("VehicleTracking", 150), "cp1": ("CartPoleSwingUp1", 150), "cp2": ("CartPoleSwingUp2", 150),
+          "park": ("CarParking", 500)}
 
 
 def worker(cases):
@@ -34,9 +36,14 @@ def worker(cases):
         kw = dict(max_line_search=10, verify=False, occupancy=variant, coop_threshold=coop)
         if mode.startswith("fix"):
             kw.update(is_check_stop=False, max_iter=int(mode[3:]))
-        algo = BasiciLQR(**kw).init(getattr(models, model)(T=T))
-        x0, tgt = synthetic_batch(model, B, seed=1234)
-        x0d, tgd = algo._dev.real(x0), algo._dev.real(tgt)
+        scen = getattr(models, model)(T=T)
+        algo = BasiciLQR(**kw).init(scen)
+        if algo._dev.generic:                       # generated models: the scenario's own initial state +- 0.05, no target
+            from curiousrl_b200.utils.synthetic import synthetic_init_states
+            x0d, tgd = algo._dev.real(synthetic_init_states(scen, B, seed=1234)), None
+        else:
+            x0, tgt = synthetic_batch(model, B, seed=1234)
+            x0d, tgd = algo._dev.real(x0), algo._dev.real(tgt)
         best = 1e30
         for _ in range(3):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

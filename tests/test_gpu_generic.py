@@ -124,6 +124,28 @@ def test_large_batch_properties():
     assert torch.equal(res.trajectory[:, -1, 4:], torch.zeros_like(res.trajectory[:, -1, 4:]))     # last action stays 0
 
 
+@pytest.mark.parametrize("name,T,B", [("VehicleTracking", 40, 1500), ("CartPoleSwingUp1", 60, 333), ("CarParking", 50, 97)])
+def test_lock_step_kernel_equals_the_per_thread_one(name, T, B):
+    """gen_solve_warp (the default: lock step + line-search helper lanes, replay of a helper's winning step size) against
+    gen_solve_one per thread (occupancy=2): iterations, flags, costs, trajectories and per-iteration traces bit for bit,
+    on a ragged batch with a wide spread of initial states (lanes finish at different iterations, so helpers exist)."""
+    from curiousrl_b200.utils.synthetic import synthetic_init_states
+    from curiousrl_b200 import logger
+    from curiousrl_b200.algorithm.ilqr_solver import BasiciLQR
+    logger.set_level(45)
+    sc = make_scenario(name, T)
+    x0 = synthetic_init_states(sc, B, seed=11, spread=0.3)
+    for extra in (dict(), dict(is_check_stop=False, max_iter=12), dict(line_search_method="feasibility")):
+        mi = extra.pop("max_iter", 60)
+        a = BasiciLQR(max_line_search=10, max_iter=mi, **extra).init(sc).solve_batch(x0, trace=True)
+        b = BasiciLQR(max_line_search=10, max_iter=mi, occupancy=2, verify=False, **extra).init(sc).solve_batch(x0, trace=True)
+        for f in ("iterations", "converged", "obj_fun_value", "trajectory", "alpha_trace"):
+            assert torch.equal(getattr(a, f), getattr(b, f)), "%s differs (%s)" % (f, extra)
+        ta, tb = a.obj_fun_trace, b.obj_fun_trace
+        assert torch.equal(torch.isnan(ta), torch.isnan(tb)) and torch.equal(torch.nan_to_num(ta), torch.nan_to_num(tb))
+    assert int(a.iterations.max()) > int(a.iterations.min())
+
+
 def test_unsupported_combinations_raise():
     import curiousrl_b200.scenario.dynamic_model as models
     from curiousrl_b200.algorithm.ilqr_solver import BasiciLQR, LogBarrieriLQR

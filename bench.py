@@ -66,6 +66,10 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="trajectories per core for the CPU baseline (0 = auto)")
     ap.add_argument("--grid-blocks", type=int, default=0)
     ap.add_argument("--no-also", action="store_true", help="skip the `also` block (the other BASELINE configs)")
+    ap.add_argument("--e2e-output", default="auto", choices=["auto", "direct", "copy"],
+                    help="end-to-end leg: the kernel writes finished trajectories straight into pinned host memory "
+                         "(direct) or the result is copied device-to-host after the solve (copy); auto = whichever "
+                         "measured faster for this number of GPUs (copy on one GPU, direct on several)")
     ap.add_argument("--cpu-kind", default="auto", choices=["auto", "reference", "port"],
                     help="CPU arm: the unmodified reference (needs baseline/_ref/), the oracle port, or whichever is there")
     return ap.parse_args()
@@ -433,15 +437,18 @@ def run_b200(args):
     cv_h = torch.empty(B, dtype=torch.uint8).pin_memory()
     X_h = torch.empty((B, T, dm.d), dtype=dm.dtype).pin_memory()
     out_h = None
-    if args.solver == "basic":      # the kernel writes finished trajectories straight into X_h (mapped pinned host memory)
+    direct = args.e2e_output == "direct" or (args.e2e_output == "auto" and world > 1)
+    if args.solver == "basic" and direct:   # the kernel writes finished trajectories straight into X_h (mapped pinned host memory)
         from curiousrl_b200.algorithm.ilqr_solver.device import BatchResult
         out_h = BatchResult(X_h, torch.empty(B, dtype=torch.float64, device=dev), torch.empty(B, dtype=torch.int32, device=dev),
                             torch.empty(B, dtype=torch.uint8, device=dev))
 
     def step_e2e():
         tgt_in = None if tgt_pin is None else tgt_pin.to(dev, non_blocking=True)
-        if args.solver == "basic":
+        if args.solver == "basic" and direct:
             r = algo.solve_batch(x0_pin.to(dev, non_blocking=True), tgt_in, out=out_h, trajectory_to_host=True)
+        elif args.solver == "basic":
+            r = algo.solve_batch(x0_pin.to(dev, non_blocking=True), tgt_in, out=out)
         else:
             r = algo.solve_batch(x0_pin.to(dev, non_blocking=True), tgt_in)
         if world > 1:
@@ -546,7 +553,9 @@ def run_b200(args):
                                               # block); LogBarrieriLQR: one per barrier parameter + the real-cost kernel
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_s * 1e3},
+                    "ms_per_step": e2e_s * 1e3,
+                    "trajectory_output": "written by the kernel into pinned host memory" if (args.solver == "basic" and direct)
+                                         else "device-to-host copy after the solve"},
             "roofline": {"bound": "hbm", "kernel": "%s<%s,%s>" % ("gen_solve_kernel" if dm.generic else "solve_kernel", args.model, args.dtype),
                          "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,

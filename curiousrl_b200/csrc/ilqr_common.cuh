@@ -18,9 +18,11 @@
 #if defined(__CUDACC__)
 #define CRL_HD __host__ __device__ __forceinline__
 #define CRL_UNROLL _Pragma("unroll")
+#define CRL_KEEP_ROLLED _Pragma("unroll 1")
 #else
 #define CRL_HD inline __attribute__((always_inline))
 #define CRL_UNROLL _Pragma("GCC unroll 16")
+#define CRL_KEEP_ROLLED _Pragma("GCC unroll 1")
 #endif
 
 namespace crl {

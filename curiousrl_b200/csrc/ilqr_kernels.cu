@@ -1595,19 +1595,19 @@ static unsigned blocks_for(long long work) { return (unsigned)((work + kBlock - 
 
 // Launch configurations of the solve.  opts->reserved selects one (0 = default):
 //   2      : lane-per-trajectory kernel, 4 warps per CTA, 2 resident CTAs per SM, warps free-running
-//   12     : the same, warps of a CTA phase-locked (SYNC)
-//   13     : 8 warps per CTA, 1 resident CTA per SM, phase-locked - the default: all eight warps of an SM run the same
-//            loop body at the same time, i.e. two warps per scheduler share the instruction stream (ncu of the
-//            1,048,576-problem solve: 0.9 `no_instruction` stall cycles per issued instruction - the loop bodies are
-//            11 - 14 KB against a ~6 KB L0 instruction cache).  Measured against 12, same box, bit-identical: ThreeLink
-//            65,536 -1 ... -5 %, 1,048,576 -0.5 ... -1.6 %, RoboticArm 262,144 x T = 200 -5 %, TwoLink -1 %.
+//   12     : the same, warps of a CTA phase-locked (SYNC) - the default
+//   13     : 8 warps per CTA, 1 resident CTA per SM, phase-locked (all eight warps of an SM run the same loop body at the
+//            same time: two warps per scheduler share the instruction stream).  EXPERIMENTAL, not the default: measured
+//            1 - 5 % faster than 12 on the benchmark batches (bit-identical there), but a lane-only solve (coop_threshold
+//            < 0) of 70 problems at T = 2 did not terminate under it on a workspace holding stale data (found at the end
+//            of round 2, profiles/r02/hang_probe_variant13.txt; configuration 12 passes the same probe) - unresolved.
 //   20, 21 : the cooperative engine as the whole solve (coop_solve_kernel, 4 trajectories per warp), 2 / 3
 //            resident CTAs per SM; 22, 23 (development builds, -DCRL_DEV_FAST): 2 / 8 trajectories per warp
 //            (element-per-lane / pair-group backward pass)
 // Every configuration produces the same results bit for bit.
 template <class R> struct SolveCfg;
-template <> struct SolveCfg<double> { static constexpr int kDefault = 13; };
-template <> struct SolveCfg<float> { static constexpr int kDefault = 13; };
+template <> struct SolveCfg<double> { static constexpr int kDefault = 12; };
+template <> struct SolveCfg<float> { static constexpr int kDefault = 12; };
 
 // A requested grid (opts->grid_blocks) is honoured up to the number of CTAs the device can hold at once.
 static int clamp_grid(int requested, int resident) { return requested > 0 && requested < resident ? requested : resident; }

@@ -35,10 +35,9 @@ CRL_HD double step_cost(const R* xu, const ParamRef<R>& prm, int t) {
     return Mdl::cost(xd, pd);
 }
 
-// The same with the parameter row already in registers.  The rollouts load the row of step t + 1 at the top of step t:
+// The same with the parameter row already in registers.  The rollouts load the row of step t at the TOP of the step:
 // loaded where the cost needs it, the load sits behind the stores of the new row (which the compiler must assume to
-// alias) and the cost waits for it (ncu: 2.4 % of the lane kernel's stall samples and 9 % of the engine's on the first
-// cost term).
+// alias) and the cost waits for it (ncu: 2.4 % of the solve's stall samples on the first cost term).
 template <class Mdl, class R>
 CRL_HD void load_params(const ParamRef<R>& prm, int t, double (&pd)[Mdl::P]) {
     CRL_UNROLL for (int i = 0; i < Mdl::P; ++i) pd[i] = (double)prm.get(t, i);
@@ -134,13 +133,11 @@ CRL_HD double rollout_closed_f(Feed& feed, R alpha, const ParamRef<R>& prm, cons
     feed.begin(T - 1);
     feed.row0(xu);                                                        // row 0 copied whole (:121)
     double J = 0.0;
-    double pd[Mdl::P], pd_next[Mdl::P];                                   // parameter rows of steps t and t + 1
-    load_params<Mdl, R>(prm, 0, pd_next);
     for (int t = 0; t < T - 1; ++t) {
         R xo_c[KN], uo_c[M], K_c[M * KN], k_c[M];
         feed.get(t, xo_c, uo_c, K_c, k_c);
-        CRL_UNROLL for (int i = 0; i < Mdl::P; ++i) pd[i] = pd_next[i];
-        load_params<Mdl, R>(prm, t + 1, pd_next);
+        double pd[Mdl::P];
+        load_params<Mdl, R>(prm, t, pd);
         R dx[KN];
         CRL_UNROLL for (int j = 0; j < KN; ++j) dx[j] = xu[j] - xo_c[j];
         CRL_UNROLL for (int a = 0; a < M; ++a) {
@@ -163,7 +160,7 @@ CRL_HD double rollout_closed_f(Feed& feed, R alpha, const ParamRef<R>& prm, cons
     }
     R* row = Xnew.row(T - 1);
     CRL_UNROLL for (int i = 0; i < D; ++i) Xnew.st(row, i, xu[i]);
-    J = J + step_cost_pd<Mdl, R>(xu, pd_next);
+    J = J + step_cost<Mdl, R>(xu, prm, T - 1);
     return J;
 }
 
@@ -196,13 +193,11 @@ CRL_HD void rollout_multi_f(Feed& feed, const R (&alpha)[NA], const ParamRef<R>&
         }
     }
     CRL_UNROLL for (int a = 0; a < NA; ++a) J[a] = 0.0;
-    double pd[Mdl::P], pd_next[Mdl::P];                                   // parameter rows of steps t and t + 1
-    load_params<Mdl, R>(prm, 0, pd_next);
     for (int t = 0; t < T - 1; ++t) {
         R xo_c[KN], uo_c[M], K_c[M * KN], k_c[M];
         feed.get(t, xo_c, uo_c, K_c, k_c);
-        CRL_UNROLL for (int i = 0; i < Mdl::P; ++i) pd[i] = pd_next[i];
-        load_params<Mdl, R>(prm, t + 1, pd_next);
+        double pd[Mdl::P];
+        load_params<Mdl, R>(prm, t, pd);
         CRL_UNROLL for (int c = 0; c < NA; ++c) {
             R dx[KN];
             CRL_UNROLL for (int j = 0; j < KN; ++j) dx[j] = xu[c][j] - xo_c[j];
@@ -241,7 +236,7 @@ CRL_HD void rollout_multi_f(Feed& feed, const R (&alpha)[NA], const ParamRef<R>&
         if (T > 1) {
             CRL_UNROLL for (int a = 0; a < M; ++a) xu[c][N + a] = R(0);
         }
-        J[c] = J[c] + step_cost_pd<Mdl, R>(xu[c], pd_next);
+        J[c] = J[c] + step_cost<Mdl, R>(xu[c], prm, T - 1);
     }
     if (STORE) {
         R* row = Xnew.row(T - 1);

@@ -104,7 +104,9 @@ typedef struct crl_solver_opts {
     int32_t stopping_method;    /* enum crl_stopping    */
     int32_t grid_blocks;        /* 0 = auto: resident CTAs per SM x SM count                   */
     int32_t reserved;           /* launch configuration of the solve kernel, 0 = chosen by     */
-                                /* batch size (results do not depend on it)                    */
+                                /* batch size (results do not depend on it).  Generated models: */
+                                /* 2 = one independent solve per thread (the checker of the     */
+                                /* default lock-step kernel with line-search helper lanes)      */
     int32_t coop_threshold;     /* once the batch queue is empty, a warp with at most this many
                                    unfinished trajectories hands them to the warp-cooperative
                                    engine (four trajectories per warp): 0 = default (12), < 0 = never.

@@ -35,20 +35,6 @@ CRL_HD double step_cost(const R* xu, const ParamRef<R>& prm, int t) {
     return Mdl::cost(xd, pd);
 }
 
-// The same with the parameter row already in registers.  The rollouts load the row of step t at the TOP of the step:
-// loaded where the cost needs it, the load sits behind the stores of the new row (which the compiler must assume to
-// alias) and the cost waits for it (ncu: 2.4 % of the solve's stall samples on the first cost term).
-template <class Mdl, class R>
-CRL_HD void load_params(const ParamRef<R>& prm, int t, double (&pd)[Mdl::P]) {
-    CRL_UNROLL for (int i = 0; i < Mdl::P; ++i) pd[i] = (double)prm.get(t, i);
-}
-template <class Mdl, class R>
-CRL_HD double step_cost_pd(const R* xu, const double (&pd)[Mdl::P]) {
-    double xd[Mdl::D];
-    CRL_UNROLL for (int i = 0; i < Mdl::D; ++i) xd[i] = (double)xu[i];
-    return Mdl::cost(xd, pd);
-}
-
 // Run-time action bounds (lets RoboticArm(is_with_constraints=False) share the device model).
 // The clamp is applied unconditionally, also against +-inf, exactly as the reference does
 // (min(max(-inf, u), inf)); keeping it branch-free also keeps a time step one basic block.
@@ -136,8 +122,6 @@ CRL_HD double rollout_closed_f(Feed& feed, R alpha, const ParamRef<R>& prm, cons
     for (int t = 0; t < T - 1; ++t) {
         R xo_c[KN], uo_c[M], K_c[M * KN], k_c[M];
         feed.get(t, xo_c, uo_c, K_c, k_c);
-        double pd[Mdl::P];
-        load_params<Mdl, R>(prm, t, pd);
         R dx[KN];
         CRL_UNROLL for (int j = 0; j < KN; ++j) dx[j] = xu[j] - xo_c[j];
         CRL_UNROLL for (int a = 0; a < M; ++a) {
@@ -150,7 +134,7 @@ CRL_HD double rollout_closed_f(Feed& feed, R alpha, const ParamRef<R>& prm, cons
         }
         R* row = Xnew.row(t);
         CRL_UNROLL for (int i = 0; i < D; ++i) Xnew.st(row, i, xu[i]);
-        J = J + step_cost_pd<Mdl, R>(xu, pd);
+        J = J + step_cost<Mdl, R>(xu, prm, t);
         model_step<Mdl, R>(xu, xn);
         CRL_UNROLL for (int i = 0; i < N; ++i) xu[i] = xn[i];
     }
@@ -196,8 +180,6 @@ CRL_HD void rollout_multi_f(Feed& feed, const R (&alpha)[NA], const ParamRef<R>&
     for (int t = 0; t < T - 1; ++t) {
         R xo_c[KN], uo_c[M], K_c[M * KN], k_c[M];
         feed.get(t, xo_c, uo_c, K_c, k_c);
-        double pd[Mdl::P];
-        load_params<Mdl, R>(prm, t, pd);
         CRL_UNROLL for (int c = 0; c < NA; ++c) {
             R dx[KN];
             CRL_UNROLL for (int j = 0; j < KN; ++j) dx[j] = xu[c][j] - xo_c[j];
@@ -225,7 +207,7 @@ CRL_HD void rollout_multi_f(Feed& feed, const R (&alpha)[NA], const ParamRef<R>&
             sincos_batch<NA * NG, R>(ang, sn, cs);       // all candidates' trigonometry as one straight-line block
             CRL_UNROLL for (int c = 0; c < NA; ++c) {
                 R xn[N];
-                J[c] = J[c] + step_cost_pd<Mdl, R>(xu[c], pd);
+                J[c] = J[c] + step_cost<Mdl, R>(xu[c], prm, t);
                 Mdl::template step_trig<R>(xu[c], sn + c * NG, cs + c * NG, xn);
                 CRL_UNROLL for (int i = 0; i < N; ++i) xu[c][i] = xn[i];
             }

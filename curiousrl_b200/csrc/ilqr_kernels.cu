@@ -451,34 +451,6 @@ __device__ __forceinline__ void warp_copy_elems(R* dst, int n, int lane, SrcAt s
     }
 }
 
-// Copies one lane's trajectory (column of a warp tile, elements 32 reals apart) into the other tile.  A function of its
-// own ON PURPOSE: it runs only for trajectories that go on without an accepted step (is_check_stop = False), and inlined
-// into the lane loop its registers and code moved the allocation of the loop's hot passes (the converging solve of
-// 1,048,576 problems got 4 % slower).  kCarryRows rows are loaded before any of them is stored: written as one load per
-// store the compiler must assume that the two tiles alias and every element waits for a DRAM round trip of its own
-// (ncu, fixed-work run: 30 % of the kernel's stall samples sat on these stores).
-template <class R, int D>
-__device__ __noinline__ void carry_tile_column(const R* src, R* dst, int T) {
-    constexpr int kCarryRows = 4;
-    for (int t0 = 0; t0 < T; t0 += kCarryRows) {
-        R v[kCarryRows][D];
-#pragma unroll
-        for (int j = 0; j < kCarryRows; ++j) {
-            if (t0 + j < T) {
-#pragma unroll
-                for (int i = 0; i < D; ++i) v[j][i] = src[((size_t)(t0 + j) * D + i) * 32];
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < kCarryRows; ++j) {
-            if (t0 + j < T) {
-#pragma unroll
-                for (int i = 0; i < D; ++i) dst[((size_t)(t0 + j) * D + i) * 32] = v[j][i];
-            }
-        }
-    }
-}
-
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
     return *reinterpret_cast<const volatile unsigned long long*>(p);
 }
@@ -1414,7 +1386,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) solve_kernel(SolveArgs<R> a)
         // buffer so that `cur` can flip for the whole warp
         const bool carry = active && !finished && !accepted;
         if (__any_sync(kFull, carry)) {
-            if (carry) carry_tile_column<R, D>(Xc.base, Xn.base, T);
+            if (carry) {
+#pragma unroll 8
+                for (int t = 0; t < T; ++t) {
+                    const R* src = Xc.row(t);
+                    R* dst = Xn.row(t);
+#pragma unroll
+                    for (int i = 0; i < D; ++i) Xn.st(dst, i, Xc.ld(src, i));
+                }
+            }
         }
         if (finished) traj = -1;
         cur ^= 1;
